@@ -1,0 +1,573 @@
+// vmig_api.cu -- the C ABI of libvmig (include/vmig.h): tree migration, buffer migration, direct
+// block hashing, the HBM-resident batch, and the host-side helpers.
+//
+// Reference seam: utils.CopyDir (utils/copy.go:21-27), moveVolumeData
+// (utils/copy.go:74-128), utils.DirSize / utils.ToBytes (utils/file.go:13-48).
+#include "vmig_engine.h"
+#include "vmig_kernels.cuh"
+#include "vmig_tree.h"
+#include "vmig_table.h"
+
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
+#include <algorithm>
+#include <thread>
+#include <cmath>
+
+using namespace vmig;
+
+namespace {
+
+inline std::string pjoin(const std::string& a, const std::string& b) { return b == "." ? a : a + "/" + b; }
+
+// ---------------------------------------------------------------------------------------------
+// file-backed BlockIO
+class FileIO : public BlockIO {
+public:
+    struct FS {
+        std::atomic<int> sfd{-1}, dfd{-1};
+        std::atomic<uint32_t> reads_left{0}, blocks_left{0};
+        bool inplace = false;            // diff path: destination file is the prior version, patched in place
+        uint64_t dst_old_size = 0;
+    };
+    std::string src_root, dst_root;
+    const Manifest* m = nullptr;
+    MetaPolicy pol;
+    bool hash_only = false;
+    std::unique_ptr<FS[]> fs;
+    std::mutex stripes[64];
+
+    int open_src(uint32_t f, int* out) {
+        FS& s = fs[f];
+        int fd = s.sfd.load(std::memory_order_acquire);
+        if (fd < 0) {
+            std::lock_guard<std::mutex> lk(stripes[f & 63]);
+            fd = s.sfd.load(std::memory_order_acquire);
+            if (fd < 0) {
+                const std::string p = pjoin(src_root, m->files[f].rel);
+                fd = open(p.c_str(), O_RDONLY | O_CLOEXEC | O_NOFOLLOW);
+                if (fd < 0) return fail(VMIG_EIO, "open %s: %s", p.c_str(), errno_str(errno).c_str());
+                s.sfd.store(fd, std::memory_order_release);
+            }
+        }
+        *out = fd; return VMIG_OK;
+    }
+    int open_dst(uint32_t f, int* out) {
+        FS& s = fs[f];
+        int fd = s.dfd.load(std::memory_order_acquire);
+        if (fd < 0) {
+            std::lock_guard<std::mutex> lk(stripes[f & 63]);
+            fd = s.dfd.load(std::memory_order_acquire);
+            if (fd < 0) {
+                const std::string p = pjoin(dst_root, m->files[f].rel);
+                if (s.inplace) {
+                    fd = open(p.c_str(), O_WRONLY | O_CLOEXEC | O_NOFOLLOW);
+                } else {
+                    bool was_dir = false;
+                    int rc = unlink_if_exists(p, &was_dir);     // tar replaces what is there
+                    if (rc) return rc;
+                    if (was_dir) return fail(VMIG_EIO, "%s: a directory is in the way of a regular file", p.c_str());
+                    fd = open(p.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_CLOEXEC | O_NOFOLLOW, 0600);
+                }
+                if (fd < 0) return fail(VMIG_EIO, "open %s for writing: %s", p.c_str(), errno_str(errno).c_str());
+                s.dfd.store(fd, std::memory_order_release);
+            }
+        }
+        *out = fd; return VMIG_OK;
+    }
+    int read_block(const BlockRef& b, uint8_t* dst) override {
+        int fd; int rc = open_src(b.file, &fd);
+        if (rc) return rc;
+        size_t got = 0;
+        while (got < b.len) {
+            ssize_t r = pread(fd, dst + got, b.len - got, (off_t)(b.file_off + got));
+            if (r < 0) { if (errno == EINTR) continue; return fail(VMIG_EIO, "pread %s: %s", m->files[b.file].rel.c_str(), errno_str(errno).c_str()); }
+            if (r == 0) return fail(VMIG_ESRCCHANGED, "%s shrank while being migrated (wanted %u bytes at %llu, got %zu)", m->files[b.file].rel.c_str(), b.len, (unsigned long long)b.file_off, got);
+            got += (size_t)r;
+        }
+        FS& s = fs[b.file];
+        if (s.reads_left.fetch_sub(1) == 1) { close(fd); s.sfd.store(-1); }
+        return VMIG_OK;
+    }
+    int write_block(const BlockRef& b, const uint8_t* src) override {
+        int fd; int rc = open_dst(b.file, &fd);
+        if (rc) return rc;
+        size_t put = 0;
+        while (put < b.len) {
+            ssize_t w = pwrite(fd, src + put, b.len - put, (off_t)(b.file_off + put));
+            if (w < 0) { if (errno == EINTR) continue; return fail(VMIG_EIO, "pwrite %s: %s", m->files[b.file].rel.c_str(), errno_str(errno).c_str()); }
+            if (w == 0) return fail(VMIG_EIO, "pwrite %s: wrote 0 bytes", m->files[b.file].rel.c_str());
+            put += (size_t)w;
+        }
+        return VMIG_OK;
+    }
+    int block_done(const BlockRef& b, bool) override {
+        FS& s = fs[b.file];
+        if (s.blocks_left.fetch_sub(1) != 1) return VMIG_OK;
+        if (hash_only) return VMIG_OK;
+        const Entry& e = m->files[b.file];
+        int fd; int rc = open_dst(b.file, &fd);      // also covers "every block was skipped"
+        if (rc) return rc;
+        const std::string p = pjoin(dst_root, e.rel);
+        if (s.inplace && s.dst_old_size != e.size && ftruncate(fd, (off_t)e.size) != 0) {
+            close(fd); return fail(VMIG_EIO, "ftruncate %s: %s", p.c_str(), errno_str(errno).c_str());
+        }
+        rc = apply_file_meta(fd, p, e, pol);
+        if (close(fd) != 0 && !rc) rc = fail(VMIG_EIO, "close %s: %s", p.c_str(), errno_str(errno).c_str());
+        s.dfd.store(-1);
+        return rc;
+    }
+    void close_all(size_t n) {
+        for (size_t i = 0; i < n; i++) {
+            int a = fs[i].sfd.exchange(-1); if (a >= 0) close(a);
+            int b = fs[i].dfd.exchange(-1); if (b >= 0) close(b);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// memory-backed BlockIO (vmig_migrate_buffer, vmig_hash_blocks)
+class MemIO : public BlockIO {
+public:
+    const uint8_t* src = nullptr; uint8_t* dst = nullptr;
+    bool src_pinned = false, dst_pinned = false;
+    int read_block(const BlockRef& b, uint8_t* d) override { if (b.len) memcpy(d, src + b.file_off, b.len); return VMIG_OK; }
+    int write_block(const BlockRef& b, const uint8_t* s) override { if (b.len) memcpy(dst + b.file_off, s, b.len); return VMIG_OK; }
+    const uint8_t* pinned_src(const BlockRef& b) override { return src_pinned ? src + b.file_off : nullptr; }
+    uint8_t* pinned_dst(const BlockRef& b) override { return dst_pinned ? dst + b.file_off : nullptr; }
+};
+
+bool is_pinned(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// ---------------------------------------------------------------------------------------------
+// run a block list over the selected GPUs (contiguous byte-balanced shares, one lane per GPU)
+int run_blocks(const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior, bool hash_only, const vmig_opts& o,
+               uint64_t* hashes, vmig_stats* st)
+{
+    std::vector<DeviceInfo> devs;
+    int rc = ctx_select(o.gpu_mask, &devs);
+    if (rc) return rc;
+    if (blocks.empty()) { st->gpus_used = 0; return VMIG_OK; }
+    size_t lanes = std::min(devs.size(), blocks.size());
+    uint64_t total = 0;
+    for (auto& b : blocks) total += std::max<uint32_t>(b.len, 4096);
+    std::vector<std::vector<BlockRef>> share(lanes);
+    {
+        uint64_t acc = 0; size_t lane = 0;
+        for (auto& b : blocks) {
+            share[lane].push_back(b);
+            acc += std::max<uint32_t>(b.len, 4096);
+            if (lane + 1 < lanes && acc >= total * (lane + 1) / lanes) lane++;
+        }
+    }
+    uint32_t readers, writers;
+    io_threads_default(&readers, &writers, o.io_threads, lanes);
+    std::vector<Pipe*> pipes(lanes, nullptr);
+    for (size_t i = 0; i < lanes; i++) {
+        rc = ctx_acquire_pipe(devs[i], &pipes[i]);
+        if (rc) { for (size_t j = 0; j < i; j++) ctx_release_pipe(pipes[j]); return rc; }
+    }
+    std::atomic<int> err{0}; std::string err_msg; std::mutex err_mu;
+    std::vector<LaneStats> ls(lanes);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < lanes; i++)
+        th.emplace_back([&, i] {
+            run_lane(pipes[i], share[i], io, has_prior, hash_only, readers, writers, hashes, &ls[i], &err, &err_msg, &err_mu);
+        });
+    for (auto& t : th) t.join();
+    for (size_t i = 0; i < lanes; i++) ctx_release_pipe(pipes[i]);
+    for (auto& l : ls) {
+        st->bytes_h2d += l.bytes_h2d; st->bytes_d2h += l.bytes_d2h; st->bytes_written += l.bytes_written;
+        st->blocks_skipped += l.blocks_skipped; st->kernel_launches += l.kernel_launches; st->ms_kernel += l.ms_kernel;
+    }
+    st->gpus_used = (uint32_t)lanes;
+    if (err.load()) { set_last_error_str(err_msg); return err.load(); }
+    return VMIG_OK;
+}
+
+vmig_opts norm_opts(const vmig_opts* in) {
+    vmig_opts o; memset(&o, 0, sizeof o);
+    if (in) o = *in;
+    if (!o.block_bytes) o.block_bytes = 4u << 20;
+    return o;
+}
+
+int migrate_tree_impl(const char* src_dir, const char* dst_dir, const char* prior_path, const char* out_path,
+                      const vmig_opts* opts_in, vmig_stats* stats_out)
+{
+    vmig_stats st; memset(&st, 0, sizeof st);
+    const uint64_t t_begin = now_ns();
+    if (!src_dir || !*src_dir) return fail(VMIG_EINVAL, "src_dir is NULL/empty");
+    vmig_opts o = norm_opts(opts_in);
+    const bool hash_only = (o.flags & VMIG_F_HASH_ONLY) != 0;
+    if (!hash_only && (!dst_dir || !*dst_dir)) return fail(VMIG_EINVAL, "dst_dir is NULL/empty");
+    if (o.block_bytes & 4095u) return fail(VMIG_EINVAL, "block_bytes %u is not a multiple of 4096", o.block_bytes);
+    if (o.block_bytes > pipe_slot_bytes()) return fail(VMIG_EINVAL, "block_bytes %u exceeds the staging slot (%u)", o.block_bytes, pipe_slot_bytes());
+    const std::string src(src_dir), dst(dst_dir ? dst_dir : "");
+    struct stat sst;
+    if (stat(src.c_str(), &sst) != 0) return fail(VMIG_EIO, "stat %s: %s", src.c_str(), errno_str(errno).c_str());
+    if (!S_ISDIR(sst.st_mode)) return fail(VMIG_ENOTDIR, "%s is not a directory", src.c_str());
+    if (!hash_only) {
+        if (stat(dst.c_str(), &sst) != 0) return fail(VMIG_EIO, "stat %s: %s", dst.c_str(), errno_str(errno).c_str());
+        if (!S_ISDIR(sst.st_mode)) return fail(VMIG_ENOTDIR, "%s is not a directory", dst.c_str());
+    }
+    // make sure a GPU is there before touching the destination: no CPU fallback
+    std::vector<DeviceInfo> devs;
+    int rc = ctx_select(o.gpu_mask, &devs);
+    if (rc) return rc;
+
+    Manifest man;
+    uint64_t t0 = now_ns();
+    rc = walk_tree(src, o.block_bytes, (o.flags & VMIG_F_SKIP_HIDDEN_TOPDIRS) != 0, &man);
+    if (rc) return rc;
+    st.ns_walk = now_ns() - t0;
+
+    t0 = now_ns();
+    BlockTable prior; bool has_prior = false;
+    if (prior_path && *prior_path && !hash_only) {
+        rc = table_load(prior_path, &prior);
+        if (rc) return rc;
+        if (prior.block_bytes != o.block_bytes) return fail(VMIG_ETABLE, "prior table block size %u != %u", prior.block_bytes, o.block_bytes);
+        has_prior = true;
+    }
+    FileIO io;
+    io.src_root = src; io.dst_root = dst; io.m = &man; io.pol = default_meta_policy(o.flags); io.hash_only = hash_only;
+    io.fs.reset(new FileIO::FS[man.files.size() ? man.files.size() : 1]);
+    std::vector<uint64_t> hashes(man.n_blocks, 0);
+
+    // ---- per-file state + block list.  Files are taken in groups of 64 (bounds open fds) and
+    // blocks round-robin across the group's files so many destination files are written at once
+    // (a single tmpfs/xfs file takes writes one thread at a time: profiles/r01_hostio_probe.txt).
+    std::vector<BlockRef> blocks; blocks.reserve(man.n_blocks);
+    std::vector<uint32_t> group;
+    auto flush_group = [&]() {
+        uint64_t maxb = 0;
+        for (uint32_t f : group) maxb = std::max(maxb, man.files[f].n_blocks);
+        for (uint64_t r = 0; r < maxb; r++)
+            for (uint32_t f : group) {
+                const Entry& e = man.files[f];
+                if (r >= e.n_blocks) continue;
+                BlockRef b; b.file = f; b.file_off = r * (uint64_t)o.block_bytes;
+                b.len = (uint32_t)std::min<uint64_t>(o.block_bytes, e.size - b.file_off);
+                b.table_idx = e.first_block + r; b.prior_hash = 0; b.prior_valid = 0;
+                if (io.fs[f].inplace) {
+                    const TableFile& pf = prior.files[prior.index[e.rel]];
+                    const uint64_t plen = r < prior.blocks_of(pf) ? std::min<uint64_t>(o.block_bytes, pf.size - b.file_off) : 0;
+                    if (plen == b.len) { b.prior_hash = prior.hashes[pf.first_block + r]; b.prior_valid = 1; }
+                }
+                blocks.push_back(b);
+            }
+        group.clear();
+    };
+    for (uint32_t f = 0; f < man.files.size(); f++) {
+        const Entry& e = man.files[f];
+        if (e.hardlink_of >= 0 || e.n_blocks == 0) continue;
+        FileIO::FS& s = io.fs[f];
+        s.reads_left.store((uint32_t)e.n_blocks); s.blocks_left.store((uint32_t)e.n_blocks);
+        if (has_prior) {
+            auto it = prior.index.find(e.rel);
+            struct stat ds;
+            if (it != prior.index.end() && lstat(pjoin(dst, e.rel).c_str(), &ds) == 0 && S_ISREG(ds.st_mode) &&
+                ds.st_nlink == 1 && (uint64_t)ds.st_size == prior.files[it->second].size) {
+                s.inplace = true; s.dst_old_size = (uint64_t)ds.st_size;
+            }
+        }
+        group.push_back(f);
+        if (group.size() == 64) flush_group();
+    }
+    flush_group();
+    st.ns_plan = now_ns() - t0;
+
+    if (!hash_only) { rc = make_dirs(dst, man); if (rc) return rc; }
+
+    t0 = now_ns();
+    rc = run_blocks(blocks, &io, has_prior, hash_only, o, hashes.data(), &st);
+    st.ns_data = now_ns() - t0;
+    if (rc) { std::string keep = last_error_cstr(); io.close_all(man.files.size()); set_last_error_str(keep); return rc; }
+
+    t0 = now_ns();
+    for (auto& e : man.files)                      // hard-linked paths share their primary's hashes
+        if (e.hardlink_of >= 0) {
+            const Entry& p = man.files[(size_t)e.hardlink_of];
+            for (uint64_t r = 0; r < e.n_blocks; r++) hashes[e.first_block + r] = hashes[p.first_block + r];
+        }
+    if (!hash_only) {
+        for (auto& e : man.files) {                // empty regular files carry no blocks
+            if (e.hardlink_of >= 0 || e.n_blocks) continue;
+            const std::string p = pjoin(dst, e.rel);
+            bool was_dir = false;
+            rc = unlink_if_exists(p, &was_dir); if (rc) return rc;
+            if (was_dir) return fail(VMIG_EIO, "%s: a directory is in the way of a regular file", p.c_str());
+            int fd = open(p.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_CLOEXEC | O_NOFOLLOW, 0600);
+            if (fd < 0) return fail(VMIG_EIO, "create %s: %s", p.c_str(), errno_str(errno).c_str());
+            rc = apply_file_meta(fd, p, e, io.pol); close(fd);
+            if (rc) return rc;
+        }
+        rc = replay_metadata(dst, man, io.pol, &st.symlinks, &st.hardlinks, &st.specials);
+        if (rc) return rc;
+    }
+    st.ns_meta = now_ns() - t0;
+
+    t0 = now_ns();
+    if (out_path && *out_path) {
+        BlockTable t; t.block_bytes = o.block_bytes; t.algo = 1;
+        t.files.reserve(man.files.size());
+        for (auto& e : man.files) t.files.push_back({e.rel, e.size, e.first_block});
+        t.hashes = hashes;
+        rc = table_store(out_path, t);
+        if (rc) return rc;
+    }
+    st.ns_table = now_ns() - t0;
+
+    if ((o.flags & VMIG_F_MOVE_SRC) && !hash_only) { rc = remove_source(src, man); if (rc) return rc; }
+
+    st.bytes_total = man.bytes_total; st.blocks_total = man.n_blocks;
+    st.files = man.files.size(); st.dirs = man.dirs.size();
+    st.ns_total = now_ns() - t_begin;
+    if (stats_out) *stats_out = st;
+    return VMIG_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int vmig_init(uint32_t gpu_mask) { return ctx_init(gpu_mask); }
+void vmig_shutdown(void) { ctx_shutdown(); }
+int vmig_device_count(void) { return ctx_device_count(); }
+const char* vmig_last_error(void) { return last_error_cstr(); }
+const char* vmig_version(void) { return "libvmig 0.1 (abi 1, sm_100a)"; }
+const char* vmig_strerror(int code)
+{
+    switch (code) {
+    case VMIG_OK: return "ok";
+    case VMIG_EINVAL: return "invalid argument";
+    case VMIG_ENOGPU: return "no usable sm_100 GPU (no CPU fallback)";
+    case VMIG_ECUDA: return "CUDA error";
+    case VMIG_EIO: return "I/O error";
+    case VMIG_ENOMEM: return "out of memory";
+    case VMIG_ETABLE: return "bad block table";
+    case VMIG_EFAULT: return "injected fault";
+    case VMIG_ENOTDIR: return "not a directory";
+    case VMIG_ESRCCHANGED: return "source changed during migration";
+    default: return "unknown vmig error";
+    }
+}
+
+int vmig_migrate_tree(const char* src_dir, const char* dst_dir, const char* prior_table, const char* out_table,
+                      const vmig_opts* opts, vmig_stats* stats)
+{
+    return migrate_tree_impl(src_dir, dst_dir, prior_table, out_table, opts, stats);
+}
+int vmig_copy_dir(const char* src_dir, const char* dst_dir) { return migrate_tree_impl(src_dir, dst_dir, nullptr, nullptr, nullptr, nullptr); }
+int vmig_move_dir(const char* src_dir, const char* dst_dir)
+{
+    vmig_opts o; memset(&o, 0, sizeof o); o.flags = VMIG_F_MOVE_SRC;
+    return migrate_tree_impl(src_dir, dst_dir, nullptr, nullptr, &o, nullptr);
+}
+
+int vmig_host_alloc(void** p, uint64_t nbytes)
+{
+    if (!p) return fail(VMIG_EINVAL, "null out pointer");
+    std::vector<DeviceInfo> devs; int rc = ctx_select(0, &devs); if (rc) return rc;
+    cudaError_t e = cudaHostAlloc(p, nbytes ? nbytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(VMIG_ENOMEM, "cudaHostAlloc(%llu): %s", (unsigned long long)nbytes, cudaGetErrorString(e)); }
+    return VMIG_OK;
+}
+void vmig_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int vmig_migrate_buffer(const void* src, void* dst, uint64_t nbytes, const uint64_t* prior_hashes, const uint8_t* prior_valid,
+                        uint64_t* out_hashes, const vmig_opts* opts, vmig_stats* stats)
+{
+    vmig_stats st; memset(&st, 0, sizeof st);
+    const uint64_t t0 = now_ns();
+    vmig_opts o = norm_opts(opts);
+    const bool hash_only = (o.flags & VMIG_F_HASH_ONLY) != 0;
+    if (!src || (!dst && !hash_only)) return fail(VMIG_EINVAL, "null buffer");
+    if ((o.block_bytes & 4095u) || o.block_bytes > pipe_slot_bytes()) return fail(VMIG_EINVAL, "bad block_bytes %u", o.block_bytes);
+    std::vector<DeviceInfo> devs; int rc = ctx_select(o.gpu_mask, &devs); if (rc) return rc;
+    const uint64_t nb = (nbytes + o.block_bytes - 1) / o.block_bytes;
+    std::vector<BlockRef> blocks(nb);
+    const bool has_prior = prior_hashes != nullptr && prior_valid != nullptr;
+    for (uint64_t i = 0; i < nb; i++) {
+        BlockRef& b = blocks[i];
+        b.file = 0; b.file_off = i * o.block_bytes; b.len = (uint32_t)std::min<uint64_t>(o.block_bytes, nbytes - b.file_off);
+        b.table_idx = i; b.prior_hash = has_prior ? prior_hashes[i] : 0; b.prior_valid = has_prior ? prior_valid[i] : 0;
+    }
+    MemIO io; io.src = (const uint8_t*)src; io.dst = (uint8_t*)dst;
+    io.src_pinned = is_pinned(src); io.dst_pinned = !hash_only && is_pinned(dst);
+    std::vector<uint64_t> hashes(nb);
+    rc = run_blocks(blocks, &io, has_prior, hash_only, o, hashes.data(), &st);
+    if (rc) return rc;
+    if (out_hashes && nb) memcpy(out_hashes, hashes.data(), nb * 8);
+    st.bytes_total = nbytes; st.blocks_total = nb; st.ns_total = st.ns_data = now_ns() - t0;
+    if (stats) *stats = st;
+    return VMIG_OK;
+}
+
+int vmig_hash_blocks(int gpu, const void* host_buf, const uint64_t* offs, const uint32_t* lens, uint64_t n,
+                     uint64_t* out_hashes, double* kernel_ms)
+{
+    if (n && (!offs || !lens || !out_hashes)) return fail(VMIG_EINVAL, "null array");
+    if (gpu < 0 || gpu > 31) return fail(VMIG_EINVAL, "bad gpu index %d", gpu);
+    vmig_opts o; memset(&o, 0, sizeof o); o.gpu_mask = 1u << gpu; o.block_bytes = 4u << 20; o.flags = VMIG_F_HASH_ONLY;
+    std::vector<DeviceInfo> devs; int rc = ctx_select(o.gpu_mask, &devs); if (rc) return rc;
+    std::vector<BlockRef> blocks(n);
+    for (uint64_t i = 0; i < n; i++) {
+        if (lens[i] && !host_buf) return fail(VMIG_EINVAL, "null host_buf");
+        blocks[i].file = 0; blocks[i].file_off = offs[i]; blocks[i].len = lens[i]; blocks[i].table_idx = i;
+        blocks[i].prior_hash = 0; blocks[i].prior_valid = 0;
+    }
+    MemIO io; io.src = (const uint8_t*)host_buf; io.dst = nullptr;   // staged: arbitrary offsets become 512-B aligned in HBM
+    vmig_stats st; memset(&st, 0, sizeof st);
+    rc = run_blocks(blocks, &io, false, true, o, out_hashes, &st);
+    if (kernel_ms) *kernel_ms = st.ms_kernel;
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// HBM-resident batch
+struct vmig_resident {
+    int dev; int sm_count; uint64_t n; uint32_t block_bytes;
+    uint8_t* d_data; uint64_t* d_offs; uint32_t* d_lens; uint64_t* d_hashes; uint64_t* d_prior; uint8_t* d_valid;
+    uint8_t* d_changed; uint32_t* d_survivors; uint32_t* d_nsurv; uint32_t* d_counter; uint64_t* d_scratch;
+    bool has_prior; cudaStream_t stream; cudaEvent_t e0, e1, e2, e3;
+};
+
+#define CU_API(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cudaGetLastError(); return fail(e__ == cudaErrorMemoryAllocation ? VMIG_ENOMEM : VMIG_ECUDA, "%s: %s", #call, cudaGetErrorString(e__)); } } while (0)
+
+int vmig_resident_open(int gpu, uint64_t n_blocks, uint32_t block_bytes, vmig_resident** out)
+{
+    if (!out || !n_blocks || !block_bytes || (block_bytes & 511u) || n_blocks > 0x7FFFFFFFull) return fail(VMIG_EINVAL, "bad resident geometry");
+    std::vector<DeviceInfo> devs; int rc = ctx_select(1u << gpu, &devs); if (rc) return rc;
+    vmig_resident* r = new vmig_resident(); memset(r, 0, sizeof *r);
+    r->dev = gpu; r->sm_count = devs[0].sm_count; r->n = n_blocks; r->block_bytes = block_bytes;
+    CU_API(cudaSetDevice(gpu));
+    CU_API(cudaMalloc((void**)&r->d_data, n_blocks * (uint64_t)block_bytes + kTailPad));
+    CU_API(cudaMalloc((void**)&r->d_offs, n_blocks * 8)); CU_API(cudaMalloc((void**)&r->d_lens, n_blocks * 4));
+    CU_API(cudaMalloc((void**)&r->d_hashes, n_blocks * 8)); CU_API(cudaMalloc((void**)&r->d_prior, n_blocks * 8));
+    CU_API(cudaMalloc((void**)&r->d_valid, n_blocks)); CU_API(cudaMalloc((void**)&r->d_changed, n_blocks));
+    CU_API(cudaMalloc((void**)&r->d_survivors, n_blocks * 4)); CU_API(cudaMalloc((void**)&r->d_nsurv, 256));
+    CU_API(cudaMalloc((void**)&r->d_counter, 256)); CU_API(cudaMalloc((void**)&r->d_scratch, n_blocks * 8));
+    CU_API(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    CU_API(cudaEventCreate(&r->e0)); CU_API(cudaEventCreate(&r->e1)); CU_API(cudaEventCreate(&r->e2)); CU_API(cudaEventCreate(&r->e3));
+    std::vector<uint64_t> offs(n_blocks); std::vector<uint32_t> lens(n_blocks, block_bytes);
+    for (uint64_t i = 0; i < n_blocks; i++) offs[i] = i * (uint64_t)block_bytes;
+    CU_API(cudaMemcpy(r->d_offs, offs.data(), n_blocks * 8, cudaMemcpyHostToDevice));
+    CU_API(cudaMemcpy(r->d_lens, lens.data(), n_blocks * 4, cudaMemcpyHostToDevice));
+    CU_API(cudaMemset(r->d_valid, 0, n_blocks)); CU_API(cudaMemset(r->d_prior, 0, n_blocks * 8));
+    CU_API(cudaMemset(r->d_data + n_blocks * (uint64_t)block_bytes, 0, kTailPad));
+    *out = r;
+    return VMIG_OK;
+}
+void vmig_resident_close(vmig_resident* r)
+{
+    if (!r) return;
+    cudaSetDevice(r->dev);
+    if (r->stream) cudaStreamSynchronize(r->stream);
+    cudaFree(r->d_data); cudaFree(r->d_offs); cudaFree(r->d_lens); cudaFree(r->d_hashes); cudaFree(r->d_prior); cudaFree(r->d_valid);
+    cudaFree(r->d_changed); cudaFree(r->d_survivors); cudaFree(r->d_nsurv); cudaFree(r->d_counter); cudaFree(r->d_scratch);
+    if (r->stream) cudaStreamDestroy(r->stream);
+    if (r->e0) cudaEventDestroy(r->e0); if (r->e1) cudaEventDestroy(r->e1); if (r->e2) cudaEventDestroy(r->e2); if (r->e3) cudaEventDestroy(r->e3);
+    delete r;
+}
+int vmig_resident_fill(vmig_resident* r, uint64_t seed)
+{
+    if (!r) return fail(VMIG_EINVAL, "null handle");
+    CU_API(cudaSetDevice(r->dev));
+    CU_API(launch_splitmix_fill(r->d_data, r->n * (uint64_t)r->block_bytes, seed, r->stream));
+    std::vector<uint32_t> lens(r->n, r->block_bytes);
+    CU_API(cudaMemcpyAsync(r->d_lens, lens.data(), r->n * 4, cudaMemcpyHostToDevice, r->stream));
+    CU_API(cudaStreamSynchronize(r->stream));
+    return VMIG_OK;
+}
+int vmig_resident_set_len(vmig_resident* r, uint64_t block, uint32_t len)
+{
+    if (!r || block >= r->n || len > r->block_bytes) return fail(VMIG_EINVAL, "bad block/len");
+    CU_API(cudaSetDevice(r->dev));
+    CU_API(cudaMemcpy(r->d_lens + block, &len, 4, cudaMemcpyHostToDevice));
+    return VMIG_OK;
+}
+int vmig_resident_upload(vmig_resident* r, uint64_t block, const void* host, uint32_t len)
+{
+    if (!r || block >= r->n || len > r->block_bytes || (len && !host)) return fail(VMIG_EINVAL, "bad block/len");
+    CU_API(cudaSetDevice(r->dev));
+    if (len) CU_API(cudaMemcpy(r->d_data + block * (uint64_t)r->block_bytes, host, len, cudaMemcpyHostToDevice));
+    CU_API(cudaMemcpy(r->d_lens + block, &len, 4, cudaMemcpyHostToDevice));
+    return VMIG_OK;
+}
+int vmig_resident_download(vmig_resident* r, uint64_t block, void* host, uint32_t len)
+{
+    if (!r || block >= r->n || len > r->block_bytes || !host) return fail(VMIG_EINVAL, "bad block/len");
+    CU_API(cudaSetDevice(r->dev));
+    CU_API(cudaMemcpy(host, r->d_data + block * (uint64_t)r->block_bytes, len, cudaMemcpyDeviceToHost));
+    return VMIG_OK;
+}
+int vmig_resident_flip(vmig_resident* r, const uint64_t* blocks, uint64_t n)
+{
+    if (!r || (n && !blocks) || n > r->n) return fail(VMIG_EINVAL, "bad flip list");
+    for (uint64_t i = 0; i < n; i++) if (blocks[i] >= r->n) return fail(VMIG_EINVAL, "flip index out of range");
+    CU_API(cudaSetDevice(r->dev));
+    if (n) {
+        CU_API(cudaMemcpyAsync(r->d_scratch, blocks, n * 8, cudaMemcpyHostToDevice, r->stream));
+        CU_API(launch_flip_first8(r->d_data, r->d_offs, r->d_scratch, n, r->stream));
+        CU_API(cudaStreamSynchronize(r->stream));
+    }
+    return VMIG_OK;
+}
+int vmig_resident_set_prior(vmig_resident* r, const uint64_t* hashes, const uint8_t* valid)
+{
+    if (!r) return fail(VMIG_EINVAL, "null handle");
+    CU_API(cudaSetDevice(r->dev));
+    r->has_prior = hashes != nullptr && valid != nullptr;
+    if (r->has_prior) {
+        CU_API(cudaMemcpy(r->d_prior, hashes, r->n * 8, cudaMemcpyHostToDevice));
+        CU_API(cudaMemcpy(r->d_valid, valid, r->n, cudaMemcpyHostToDevice));
+    } else {
+        CU_API(cudaMemset(r->d_valid, 0, r->n));
+    }
+    return VMIG_OK;
+}
+int vmig_resident_pass(vmig_resident* r, uint32_t iters, double* ms_hash_last, double* ms_total)
+{
+    if (!r || !iters) return fail(VMIG_EINVAL, "bad arguments");
+    CU_API(cudaSetDevice(r->dev));
+    HashLaunch a;
+    a.base = r->d_data; a.offs = r->d_offs; a.lens = r->d_lens; a.n = (uint32_t)r->n; a.hashes = r->d_hashes;
+    a.prior = r->d_prior; a.prior_valid = r->d_valid; a.changed = r->d_changed; a.work_counter = r->d_counter;
+    CU_API(cudaEventRecord(r->e0, r->stream));
+    for (uint32_t it = 0; it < iters; it++) {
+        if (it + 1 == iters) CU_API(cudaEventRecord(r->e1, r->stream));
+        CU_API(launch_xxh64_blocks(a, r->sm_count, r->stream));
+        if (it + 1 == iters) CU_API(cudaEventRecord(r->e2, r->stream));
+        CU_API(launch_diff_select(r->d_changed, (uint32_t)r->n, r->d_survivors, r->d_nsurv, r->stream));
+    }
+    CU_API(cudaEventRecord(r->e3, r->stream));
+    CU_API(cudaStreamSynchronize(r->stream));
+    float a_ms = 0, b_ms = 0;
+    CU_API(cudaEventElapsedTime(&a_ms, r->e1, r->e2));
+    CU_API(cudaEventElapsedTime(&b_ms, r->e0, r->e3));
+    if (ms_hash_last) *ms_hash_last = a_ms;
+    if (ms_total) *ms_total = b_ms;
+    return VMIG_OK;
+}
+int vmig_resident_results(vmig_resident* r, uint64_t* hashes, uint32_t* survivors, uint64_t* n_survivors)
+{
+    if (!r) return fail(VMIG_EINVAL, "null handle");
+    CU_API(cudaSetDevice(r->dev));
+    if (hashes) CU_API(cudaMemcpy(hashes, r->d_hashes, r->n * 8, cudaMemcpyDeviceToHost));
+    uint32_t ns = 0;
+    CU_API(cudaMemcpy(&ns, r->d_nsurv, 4, cudaMemcpyDeviceToHost));
+    if (n_survivors) *n_survivors = ns;
+    if (survivors && ns) CU_API(cudaMemcpy(survivors, r->d_survivors, (size_t)ns * 4, cudaMemcpyDeviceToHost));
+    return VMIG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,589 @@
+// vmig_engine.cu -- process-wide GPU context, pinned/HBM slot pools and the per-GPU streaming
+// pipeline (see vmig_engine.h for the data flow).  Replaces the byte-moving loop of the
+// reference's `tar c | tar x` pipe (utils/copy.go:17-27) and of `mv` in the helper container
+// (utils/copy.go:116); everything here is new design, there is no reference counterpart.
+#include "vmig_engine.h"
+#include "vmig_kernels.cuh"
+
+#include <sched.h>
+#include <unistd.h>
+#include <sys/resource.h>
+#include <condition_variable>
+#include <deque>
+#include <thread>
+#include <fstream>
+#include <sstream>
+#include <algorithm>
+#include <cstdlib>
+
+namespace vmig {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+static thread_local std::string g_last_error;
+void set_last_error_str(const std::string& s) { g_last_error = s; }
+void set_last_error(const char* fmt, ...) {
+    char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap); g_last_error = buf;
+}
+const char* last_error_cstr() { return g_last_error.c_str(); }
+long env_long(const char* name, long dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    char* end = nullptr; long r = strtol(v, &end, 10);
+    return end && *end == 0 ? r : dflt;
+}
+
+#define CU_TRY(call)                                                                                  \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(e__ == cudaErrorMemoryAllocation ? VMIG_ENOMEM : VMIG_ECUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e__));                                                     \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// tunables (env, read once per process)
+static constexpr uint32_t kMaxBatchBlocks = 4096;
+static uint32_t g_slot_bytes = 0, g_slots = 0, g_pipes_per_gpu = 0;
+static void load_tunables() {
+    if (g_slot_bytes) return;
+    long mb = env_long("VMIG_SLOT_MB", 32);
+    if (mb < 4) mb = 4; if (mb > 1024) mb = 1024;
+    long ns = env_long("VMIG_SLOTS", 16);
+    if (ns < 2) ns = 2; if (ns > 64) ns = 64;
+    long pp = env_long("VMIG_PIPES_PER_GPU", 2);
+    if (pp < 1) pp = 1; if (pp > 8) pp = 8;
+    g_slots = (uint32_t)ns; g_pipes_per_gpu = (uint32_t)pp;
+    g_slot_bytes = (uint32_t)(mb << 20);
+}
+uint32_t pipe_slot_bytes() { load_tunables(); return g_slot_bytes; }
+
+// ---------------------------------------------------------------------------------------------
+// slot / pipe
+struct Slot {
+    uint8_t* h_in = nullptr;    // pinned, slot_bytes + pad
+    uint8_t* h_out = nullptr;   // pinned, slot_bytes + pad
+    uint8_t* d_buf = nullptr;   // HBM,    slot_bytes + pad
+    uint8_t* h_desc = nullptr;  // pinned: packed [offs u64][prior u64][lens u32][valid u8] for n blocks
+    uint8_t* d_desc = nullptr;
+    uint8_t* h_res = nullptr;   // pinned: packed [hashes u64][changed u8]
+    uint8_t* d_res = nullptr;
+    uint32_t* d_counter = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_hash = nullptr, ev_d2h = nullptr;
+};
+static constexpr size_t kDescBytes = (size_t)kMaxBatchBlocks * (8 + 8 + 4 + 1) + 64;
+static constexpr size_t kResBytes  = (size_t)kMaxBatchBlocks * (8 + 1) + 64;
+
+class Pipe {
+public:
+    DeviceInfo dev;
+    uint32_t slot_bytes = 0;
+    std::vector<Slot> slots;
+    int create(const DeviceInfo& d);
+    void destroy();
+};
+
+int Pipe::create(const DeviceInfo& d)
+{
+    load_tunables();
+    dev = d; slot_bytes = g_slot_bytes;
+    CU_TRY(cudaSetDevice(d.dev));
+    slots.resize(g_slots);
+    const size_t cap = (size_t)slot_bytes + kTailPad;
+    for (auto& s : slots) {
+        CU_TRY(cudaHostAlloc((void**)&s.h_in, cap, cudaHostAllocPortable));
+        CU_TRY(cudaHostAlloc((void**)&s.h_out, cap, cudaHostAllocPortable));
+        CU_TRY(cudaMalloc((void**)&s.d_buf, cap));
+        CU_TRY(cudaMemset(s.d_buf, 0, cap));
+        CU_TRY(cudaHostAlloc((void**)&s.h_desc, kDescBytes, cudaHostAllocPortable));
+        CU_TRY(cudaMalloc((void**)&s.d_desc, kDescBytes));
+        CU_TRY(cudaHostAlloc((void**)&s.h_res, kResBytes, cudaHostAllocPortable));
+        CU_TRY(cudaMalloc((void**)&s.d_res, kResBytes));
+        CU_TRY(cudaMalloc((void**)&s.d_counter, 256));
+        CU_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreate(&s.ev_k0)); CU_TRY(cudaEventCreate(&s.ev_k1));
+        CU_TRY(cudaEventCreateWithFlags(&s.ev_hash, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
+        memset(s.h_in, 0, cap); memset(s.h_out, 0, cap);    // fault the pinned pages in now
+    }
+    CU_TRY(cudaDeviceSynchronize());
+    return VMIG_OK;
+}
+void Pipe::destroy()
+{
+    cudaSetDevice(dev.dev);
+    for (auto& s : slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFreeHost(s.h_in); cudaFreeHost(s.h_out); cudaFree(s.d_buf); cudaFreeHost(s.h_desc); cudaFree(s.d_desc);
+        cudaFreeHost(s.h_res); cudaFree(s.d_res); cudaFree(s.d_counter);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.ev_k0) cudaEventDestroy(s.ev_k0); if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+        if (s.ev_hash) cudaEventDestroy(s.ev_hash); if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+    }
+    slots.clear();
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+struct DevPool {
+    DeviceInfo info;
+    std::vector<Pipe*> free_pipes;
+    uint32_t n_pipes = 0;
+};
+static std::mutex g_mu;
+static std::condition_variable g_cv;
+static bool g_inited = false;
+static std::vector<DevPool> g_devs;
+
+static std::vector<int> parse_cpulist(const std::string& s) {
+    std::vector<int> out; std::stringstream ss(s); std::string tok;
+    while (std::getline(ss, tok, ',')) {
+        int a, b;
+        if (sscanf(tok.c_str(), "%d-%d", &a, &b) == 2) { for (int i = a; i <= b; i++) out.push_back(i); }
+        else if (sscanf(tok.c_str(), "%d", &a) == 1) out.push_back(a);
+    }
+    return out;
+}
+static std::vector<int> gpu_local_cpus(int dev) {
+    if (env_long("VMIG_NUMA", 1) == 0) return {};
+    char bus[64] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, dev) != cudaSuccess) { cudaGetLastError(); return {}; }
+    for (char* p = bus; *p; p++) *p = (char)tolower(*p);
+    std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist");
+    std::string line;
+    if (!f || !std::getline(f, line)) return {};
+    std::vector<int> cpus = parse_cpulist(line);
+    // intersect with what this process may run on
+    cpu_set_t cur; CPU_ZERO(&cur);
+    if (sched_getaffinity(0, sizeof cur, &cur) == 0) {
+        std::vector<int> keep; for (int c : cpus) if (c < CPU_SETSIZE && CPU_ISSET(c, &cur)) keep.push_back(c);
+        cpus.swap(keep);
+    }
+    return cpus;
+}
+
+int ctx_device_count()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return fail(VMIG_ENOGPU, "no CUDA device (%s); libvmig has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count 0"); }
+    int ok = 0;
+    for (int i = 0; i < n; i++) { cudaDeviceProp p; if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++; }
+    if (!ok) return fail(VMIG_ENOGPU, "no sm_100 (Blackwell B200) device among %d CUDA devices; libvmig ships sm_100a code only", n);
+    return ok;
+}
+
+int ctx_init(uint32_t gpu_mask)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    load_tunables();
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return fail(VMIG_ENOGPU, "no CUDA device (%s); libvmig has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count 0"); }
+    if (!g_inited) {
+        struct rlimit rl;
+        if (getrlimit(RLIMIT_NOFILE, &rl) == 0 && rl.rlim_cur < rl.rlim_max) { rl.rlim_cur = rl.rlim_max; setrlimit(RLIMIT_NOFILE, &rl); }
+    }
+    int added = 0;
+    for (int i = 0; i < n && i < 32; i++) {
+        if (gpu_mask && !(gpu_mask & (1u << i))) continue;
+        bool have = false;
+        for (auto& d : g_devs) if (d.info.dev == i) have = true;
+        if (have) { added++; continue; }
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (p.major != 10) continue;          // sm_100a SASS only
+        DevPool dp; dp.info.dev = i; dp.info.sm_count = p.multiProcessorCount; dp.info.cpus = gpu_local_cpus(i);
+        g_devs.push_back(dp);
+        added++;
+    }
+    if (!added && g_devs.empty()) return fail(VMIG_ENOGPU, "no sm_100 device selected by mask 0x%x (%d CUDA devices)", gpu_mask, n);
+    std::sort(g_devs.begin(), g_devs.end(), [](const DevPool& a, const DevPool& b) { return a.info.dev < b.info.dev; });
+    g_inited = true;
+    return VMIG_OK;
+}
+
+void ctx_shutdown()
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& d : g_devs) {
+        for (Pipe* p : d.free_pipes) { p->destroy(); delete p; }
+        d.free_pipes.clear(); d.n_pipes = 0;
+    }
+    g_devs.clear();
+    g_inited = false;
+}
+
+int ctx_select(uint32_t mask, std::vector<DeviceInfo>* out)
+{
+    {
+        std::unique_lock<std::mutex> lk(g_mu);
+        bool need = !g_inited;
+        if (!need && mask) for (int i = 0; i < 32; i++) if (mask & (1u << i)) { bool have = false; for (auto& d : g_devs) if (d.info.dev == i) have = true; if (!have) need = true; }
+        if (need) { lk.unlock(); int rc = ctx_init(mask); if (rc) return rc; }
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    out->clear();
+    for (auto& d : g_devs) if (!mask || (mask & (1u << d.info.dev))) out->push_back(d.info);
+    if (out->empty()) return fail(VMIG_ENOGPU, "gpu_mask 0x%x selects no initialised sm_100 device", mask);
+    return VMIG_OK;
+}
+
+int ctx_acquire_pipe(const DeviceInfo& d, Pipe** out)
+{
+    std::unique_lock<std::mutex> lk(g_mu);
+    for (;;) {
+        DevPool* dp = nullptr;
+        for (auto& x : g_devs) if (x.info.dev == d.dev) dp = &x;
+        if (!dp) return fail(VMIG_ENOGPU, "device %d not initialised", d.dev);
+        if (!dp->free_pipes.empty()) { *out = dp->free_pipes.back(); dp->free_pipes.pop_back(); return VMIG_OK; }
+        if (dp->n_pipes < g_pipes_per_gpu) {
+            dp->n_pipes++;
+            lk.unlock();
+            Pipe* p = new Pipe();
+            int rc = p->create(d);
+            if (rc) {
+                std::string keep = last_error_cstr();
+                p->destroy(); delete p; lk.lock();
+                for (auto& x : g_devs) if (x.info.dev == d.dev) x.n_pipes--;
+                g_cv.notify_all(); set_last_error_str(keep);
+                return rc;
+            }
+            *out = p;
+            return VMIG_OK;
+        }
+        g_cv.wait(lk);
+    }
+}
+void ctx_release_pipe(Pipe* p)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& x : g_devs) if (x.info.dev == p->dev.dev) { x.free_pipes.push_back(p); g_cv.notify_all(); return; }
+    p->destroy(); delete p;    // context was shut down underneath us
+}
+
+int io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested, size_t lanes)
+{
+    long r = env_long("VMIG_READERS", 0), w = env_long("VMIG_WRITERS", 0);
+    if (requested) { r = (requested + 1) * 2 / 5; w = requested - r; }
+    if (r <= 0 || w <= 0) {
+        cpu_set_t cur; CPU_ZERO(&cur);
+        long ncpu = sched_getaffinity(0, sizeof cur, &cur) == 0 ? CPU_COUNT(&cur) : sysconf(_SC_NPROCESSORS_ONLN);
+        int ngpu = 1; if (cudaGetDeviceCount(&ngpu) != cudaSuccess) { cudaGetLastError(); ngpu = 1; }
+        long share = std::max<long>(lanes, (size_t)ngpu);         // other GPUs may be busy migrating too
+        long budget = std::min<long>(32, std::max<long>(4, ncpu / share));
+        if (r <= 0) r = std::max<long>(2, budget * 3 / 8);
+        if (w <= 0) w = std::max<long>(2, budget - r);
+    }
+    *readers = (uint32_t)std::min<long>(r, 64); *writers = (uint32_t)std::min<long>(w, 64);
+    return VMIG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// blocking queue
+template <class T>
+class BQ {
+    std::mutex mu; std::condition_variable cv; std::deque<T> q; bool closed = false;
+public:
+    void push(T v) { { std::lock_guard<std::mutex> lk(mu); q.push_back(std::move(v)); } cv.notify_one(); }
+    bool pop(T* out) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return closed || !q.empty(); });
+        if (q.empty()) return false;
+        *out = std::move(q.front()); q.pop_front(); return true;
+    }
+    void close() { { std::lock_guard<std::mutex> lk(mu); closed = true; } cv.notify_all(); }
+};
+
+struct Batch {
+    size_t b0 = 0, b1 = 0;          // block range in the lane's list
+    size_t bytes_used = 0;          // staged bytes (aligned layout) in the slot
+    int slot = -1;
+    std::atomic<int> reads_left{0}, writes_left{0};
+    bool failed = false;
+    std::vector<uint8_t> survive;   // per block, filled after hashing
+};
+struct IoTask { Batch* batch; size_t i0, i1; };
+
+static void bind_thread(const DeviceInfo& d) {
+    if (d.cpus.empty()) return;
+    cpu_set_t set; CPU_ZERO(&set);
+    for (int c : d.cpus) if (c < CPU_SETSIZE) CPU_SET(c, &set);
+    sched_setaffinity(0, sizeof set, &set);
+}
+
+int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior, bool hash_only,
+             uint32_t n_readers, uint32_t n_writers, uint64_t* hashes_out, LaneStats* stats,
+             std::atomic<int>* err, std::string* err_msg, std::mutex* err_mu)
+{
+    if (blocks.empty()) return VMIG_OK;
+    const uint32_t slot_bytes = pipe->slot_bytes;
+    const long fail_block = env_long("VMIG_FAIL_BLOCK", -1);
+
+    auto set_err = [&](int code) {
+        int expect = 0;
+        if (err->compare_exchange_strong(expect, code)) { std::lock_guard<std::mutex> lk(*err_mu); *err_msg = last_error_cstr(); }
+    };
+
+    // ---- plan: pack consecutive blocks into slot-sized batches, 512-B aligned
+    std::vector<uint32_t> slot_off(blocks.size());
+    std::vector<std::unique_ptr<Batch>> batches;
+    {
+        size_t i = 0;
+        while (i < blocks.size()) {
+            auto b = std::make_unique<Batch>();
+            b->b0 = i; size_t used = 0;
+            while (i < blocks.size() && (i - b->b0) < kMaxBatchBlocks) {
+                const size_t need = align_up(std::max<uint32_t>(blocks[i].len, 1), kBlockAlign);
+                if (need > slot_bytes) { set_last_error("block of %u bytes exceeds the %u-byte staging slot (VMIG_SLOT_MB)", blocks[i].len, slot_bytes); return VMIG_EINVAL; }
+                if (used + need > slot_bytes) break;
+                slot_off[i] = (uint32_t)used; used += need; i++;
+            }
+            b->b1 = i; b->bytes_used = used;
+            batches.push_back(std::move(b));
+        }
+    }
+    const size_t n_batches = batches.size();
+
+    BQ<int> free_slots;
+    for (int s = 0; s < (int)pipe->slots.size(); s++) free_slots.push(s);
+    BQ<IoTask> read_q, write_q;
+    BQ<Batch*> submit_q, hashwait_q, d2hwait_q;
+    std::mutex done_mu; std::condition_variable done_cv; size_t batches_done = 0;
+    std::mutex stat_mu;
+
+    auto finish_batch = [&](Batch* b) {
+        free_slots.push(b->slot);
+        std::lock_guard<std::mutex> lk(done_mu);
+        if (++batches_done == n_batches) done_cv.notify_all();
+    };
+    const bool direct_src = io->pinned_src(blocks[0]) != nullptr;
+    const bool direct_dst = !hash_only && io->pinned_dst(blocks[0]) != nullptr;
+
+    // ---- stage 1: dispatcher -> read tasks
+    std::thread dispatcher([&] {
+        bind_thread(pipe->dev);
+        for (auto& bp : batches) {
+            Batch* b = bp.get();
+            int s;
+            if (!free_slots.pop(&s)) return;
+            b->slot = s;
+            if (direct_src || err->load()) { b->failed = err->load() != 0; submit_q.push(b); continue; }
+            // group small blocks so a task carries >= 1 MiB or 64 blocks
+            std::vector<IoTask> tasks;
+            size_t i = b->b0;
+            while (i < b->b1) {
+                size_t j = i, bytes = 0;
+                while (j < b->b1 && (j - i) < 64 && bytes < (1u << 20)) { bytes += blocks[j].len; j++; }
+                tasks.push_back({b, i, j}); i = j;
+            }
+            b->reads_left.store((int)tasks.size());
+            for (auto& t : tasks) read_q.push(t);
+        }
+    });
+
+    // ---- stage 2: readers
+    std::vector<std::thread> readers;
+    for (uint32_t t = 0; t < n_readers; t++)
+        readers.emplace_back([&] {
+            bind_thread(pipe->dev);
+            IoTask k;
+            while (read_q.pop(&k)) {
+                Slot& sl = pipe->slots[k.batch->slot];
+                if (!err->load())
+                    for (size_t i = k.i0; i < k.i1; i++) {
+                        int rc = io->read_block(blocks[i], sl.h_in + slot_off[i]);
+                        if (rc) { set_err(rc); break; }
+                    }
+                if (k.batch->reads_left.fetch_sub(1) == 1) submit_q.push(k.batch);
+            }
+        });
+
+    // ---- stage 3: submit H2D + kernel (+ D2H) on the slot's side stream
+    auto submit_one = [&](Batch* b) -> int {
+        Slot& sl = pipe->slots[b->slot];
+        const uint32_t n = (uint32_t)(b->b1 - b->b0);
+        uint64_t* h_offs = (uint64_t*)sl.h_desc; uint64_t* h_prior = h_offs + n;
+        uint32_t* h_lens = (uint32_t*)(h_prior + n); uint8_t* h_valid = (uint8_t*)(h_lens + n);
+        for (uint32_t i = 0; i < n; i++) {
+            const BlockRef& r = blocks[b->b0 + i];
+            h_offs[i] = slot_off[b->b0 + i]; h_prior[i] = r.prior_hash; h_lens[i] = r.len; h_valid[i] = r.prior_valid;
+        }
+        const size_t desc_bytes = (size_t)n * 21;
+        CU_TRY(cudaMemcpyAsync(sl.d_desc, sl.h_desc, desc_bytes, cudaMemcpyHostToDevice, sl.stream));
+        uint64_t h2d = 0;
+        if (direct_src) {
+            for (uint32_t i = 0; i < n; i++) {
+                const BlockRef& r = blocks[b->b0 + i];
+                if (!r.len) continue;
+                CU_TRY(cudaMemcpyAsync(sl.d_buf + slot_off[b->b0 + i], io->pinned_src(r), r.len, cudaMemcpyHostToDevice, sl.stream));
+                h2d += r.len;
+            }
+        } else {
+            CU_TRY(cudaMemcpyAsync(sl.d_buf, sl.h_in, b->bytes_used, cudaMemcpyHostToDevice, sl.stream));
+            for (uint32_t i = 0; i < n; i++) h2d += blocks[b->b0 + i].len;
+        }
+        HashLaunch a;
+        a.base = sl.d_buf; a.offs = (const uint64_t*)sl.d_desc; a.prior = a.offs + n;
+        a.lens = (const uint32_t*)(a.prior + n); a.prior_valid = (const uint8_t*)(a.lens + n);
+        a.n = n; a.hashes = (uint64_t*)sl.d_res; a.changed = (uint8_t*)(a.hashes + n);
+        a.work_counter = sl.d_counter;
+        if (!has_prior) { a.prior = nullptr; a.prior_valid = nullptr; }
+        CU_TRY(cudaEventRecord(sl.ev_k0, sl.stream));
+        CU_TRY(launch_xxh64_blocks(a, pipe->dev.sm_count, sl.stream));
+        CU_TRY(cudaEventRecord(sl.ev_k1, sl.stream));
+        CU_TRY(cudaMemcpyAsync(sl.h_res, sl.d_res, (size_t)n * 9, cudaMemcpyDeviceToHost, sl.stream));
+        CU_TRY(cudaEventRecord(sl.ev_hash, sl.stream));
+        uint64_t d2h = 0;
+        if (!has_prior && !hash_only) {       // every block survives: stream it back right away
+            if (direct_dst) {
+                for (uint32_t i = 0; i < n; i++) {
+                    const BlockRef& r = blocks[b->b0 + i];
+                    if (!r.len) continue;
+                    CU_TRY(cudaMemcpyAsync(io->pinned_dst(r), sl.d_buf + slot_off[b->b0 + i], r.len, cudaMemcpyDeviceToHost, sl.stream));
+                    d2h += r.len;
+                }
+            } else {
+                CU_TRY(cudaMemcpyAsync(sl.h_out, sl.d_buf, b->bytes_used, cudaMemcpyDeviceToHost, sl.stream));
+                d2h = h2d;
+            }
+            CU_TRY(cudaEventRecord(sl.ev_d2h, sl.stream));
+        }
+        std::lock_guard<std::mutex> lk(stat_mu);
+        stats->bytes_h2d += h2d; stats->bytes_d2h += d2h; stats->kernel_launches += 1;
+        return VMIG_OK;
+    };
+    std::thread submitter([&] {
+        bind_thread(pipe->dev);
+        cudaSetDevice(pipe->dev.dev);
+        Batch* b;
+        while (submit_q.pop(&b)) {
+            if (err->load()) b->failed = true;
+            if (!b->failed) { int rc = submit_one(b); if (rc) { set_err(rc); b->failed = true; } }
+            hashwait_q.push(b);
+        }
+    });
+
+    // ---- stage 4: wait for hashes, pick survivors, issue their D2H
+    auto after_hash = [&](Batch* b) -> int {
+        Slot& sl = pipe->slots[b->slot];
+        const uint32_t n = (uint32_t)(b->b1 - b->b0);
+        CU_TRY(cudaEventSynchronize(sl.ev_hash));
+        float ms = 0; CU_TRY(cudaEventElapsedTime(&ms, sl.ev_k0, sl.ev_k1));
+        const uint64_t* h_hash = (const uint64_t*)sl.h_res; const uint8_t* h_changed = (const uint8_t*)(h_hash + n);
+        b->survive.assign(n, 1);
+        uint64_t skipped = 0, d2h = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            const BlockRef& r = blocks[b->b0 + i];
+            hashes_out[r.table_idx] = h_hash[i];
+            if (fail_block >= 0 && (uint64_t)fail_block == r.table_idx) return fail(VMIG_EFAULT, "injected fault at block %ld (VMIG_FAIL_BLOCK)", fail_block);
+            if (has_prior && !h_changed[i]) { b->survive[i] = 0; skipped++; }
+        }
+        if (has_prior && !hash_only) {
+            uint32_t i = 0;
+            while (i < n) {      // coalesce runs of adjacent survivors into one DMA
+                if (!b->survive[i] || !blocks[b->b0 + i].len) { i++; continue; }
+                if (direct_dst) {
+                    const BlockRef& r = blocks[b->b0 + i];
+                    CU_TRY(cudaMemcpyAsync(io->pinned_dst(r), sl.d_buf + slot_off[b->b0 + i], r.len, cudaMemcpyDeviceToHost, sl.stream));
+                    d2h += r.len; i++; continue;
+                }
+                uint32_t j = i; size_t start = slot_off[b->b0 + i], end = start;
+                while (j < n && b->survive[j]) { end = slot_off[b->b0 + j] + blocks[b->b0 + j].len; d2h += blocks[b->b0 + j].len; j++; }
+                CU_TRY(cudaMemcpyAsync(sl.h_out + start, sl.d_buf + start, end - start, cudaMemcpyDeviceToHost, sl.stream));
+                i = j;
+            }
+            CU_TRY(cudaEventRecord(sl.ev_d2h, sl.stream));
+        }
+        std::lock_guard<std::mutex> lk(stat_mu);
+        stats->ms_kernel += ms; stats->blocks_skipped += skipped; stats->bytes_d2h += d2h;
+        return VMIG_OK;
+    };
+    std::thread hashwaiter([&] {
+        bind_thread(pipe->dev);
+        cudaSetDevice(pipe->dev.dev);
+        Batch* b;
+        while (hashwait_q.pop(&b)) {
+            if (err->load()) b->failed = true;
+            if (!b->failed) { int rc = after_hash(b); if (rc) { set_err(rc); b->failed = true; } }
+            if (b->failed) b->survive.assign(b->b1 - b->b0, 0);
+            d2hwait_q.push(b);
+        }
+    });
+
+    // ---- stage 5: wait for the survivors' D2H, hand them to the writers
+    std::thread d2hwaiter([&] {
+        bind_thread(pipe->dev);
+        cudaSetDevice(pipe->dev.dev);
+        Batch* b;
+        while (d2hwait_q.pop(&b)) {
+            Slot& sl = pipe->slots[b->slot];
+            if (!b->failed && !hash_only) {
+                cudaError_t e = cudaEventSynchronize(sl.ev_d2h);
+                if (e != cudaSuccess) { fail(VMIG_ECUDA, "cudaEventSynchronize(d2h): %s", cudaGetErrorString(e)); set_err(VMIG_ECUDA); b->failed = true; }
+            }
+            const size_t n = b->b1 - b->b0;
+            std::vector<IoTask> tasks;
+            if (!b->failed && !hash_only && !direct_dst) {
+                size_t i = 0;
+                while (i < n) {
+                    if (!b->survive[i]) { i++; continue; }
+                    size_t j = i, bytes = 0;
+                    while (j < n && b->survive[j] && (j - i) < 64 && bytes < (1u << 20)) { bytes += blocks[b->b0 + j].len; j++; }
+                    tasks.push_back({b, b->b0 + i, b->b0 + j}); i = j;
+                }
+            }
+            // blocks that need no write are complete now
+            for (size_t i = 0; i < n; i++) {
+                const bool written_later = !tasks.empty() && b->survive[i];
+                if (!written_later) {
+                    const bool was_written = !b->failed && !hash_only && direct_dst && b->survive[i];
+                    if (b->failed) continue;            // do not finalize files of a failed call
+                    int rc = io->block_done(blocks[b->b0 + i], was_written);
+                    if (rc) set_err(rc);
+                    if (was_written) { std::lock_guard<std::mutex> lk(stat_mu); stats->bytes_written += blocks[b->b0 + i].len; }
+                }
+            }
+            if (tasks.empty()) { finish_batch(b); continue; }
+            b->writes_left.store((int)tasks.size());
+            for (auto& t : tasks) write_q.push(t);
+        }
+    });
+
+    // ---- stage 6: writers
+    std::vector<std::thread> writers;
+    for (uint32_t t = 0; t < n_writers; t++)
+        writers.emplace_back([&] {
+            bind_thread(pipe->dev);
+            IoTask k;
+            while (write_q.pop(&k)) {
+                Slot& sl = pipe->slots[k.batch->slot];
+                uint64_t wrote = 0;
+                for (size_t i = k.i0; i < k.i1; i++) {
+                    if (err->load()) break;
+                    int rc = io->write_block(blocks[i], sl.h_out + slot_off[i]);
+                    if (!rc) { wrote += blocks[i].len; rc = io->block_done(blocks[i], true); }
+                    if (rc) { set_err(rc); break; }
+                }
+                { std::lock_guard<std::mutex> lk(stat_mu); stats->bytes_written += wrote; }
+                if (k.batch->writes_left.fetch_sub(1) == 1) finish_batch(k.batch);
+            }
+        });
+
+    {
+        std::unique_lock<std::mutex> lk(done_mu);
+        done_cv.wait(lk, [&] { return batches_done == n_batches; });
+    }
+    read_q.close(); submit_q.close(); hashwait_q.close(); d2hwait_q.close(); write_q.close(); free_slots.close();
+    dispatcher.join();
+    for (auto& t : readers) t.join();
+    submitter.join(); hashwaiter.join(); d2hwaiter.join();
+    for (auto& t : writers) t.join();
+    // the slots go back to the pool idle
+    cudaSetDevice(pipe->dev.dev);
+    for (auto& s : pipe->slots) cudaStreamSynchronize(s.stream);
+    return err->load();
+}
+
+}  // namespace vmig

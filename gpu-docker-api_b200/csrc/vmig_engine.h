@@ -1,0 +1,76 @@
+// vmig_engine.h -- per-GPU streaming pipeline of libvmig (internal interface).
+//
+//   source blocks --(reader threads: pread / memcpy)--> pinned IN slot
+//       --cudaMemcpyAsync H2D (slot's side stream)--> HBM slot
+//       --xxh64_blocks kernel (+ compare with prior table)--> hashes, changed flags
+//       --cudaMemcpyAsync D2H of the surviving blocks--> pinned OUT slot
+//       --(writer threads: pwrite / memcpy)--> destination
+//
+// One Pipe owns kSlots such slot triples on one GPU; a lane (one GPU's share of one call) checks
+// a Pipe out of the process-wide pool, runs its block list through it and returns it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "vmig_common.h"
+
+namespace vmig {
+
+struct BlockRef {
+    uint32_t file;         // backend-defined (index of the file in the manifest; 0 for buffers)
+    uint32_t len;          // bytes in this block (<= block_bytes; 0 allowed)
+    uint64_t file_off;     // byte offset inside the file / buffer
+    uint64_t table_idx;    // where this block's hash goes in the call-wide hash array
+    uint64_t prior_hash;   // prior version's hash of the same block ...
+    uint8_t  prior_valid;  // ... if 1
+};
+
+// Where block bytes come from and go to.  Implementations must be thread-safe.
+class BlockIO {
+public:
+    virtual ~BlockIO() {}
+    virtual int  read_block(const BlockRef& b, uint8_t* dst) = 0;
+    virtual int  write_block(const BlockRef& b, const uint8_t* src) = 0;
+    // called exactly once per block when it needs nothing more (written == false: skipped)
+    virtual int  block_done(const BlockRef&, bool /*written*/) { return VMIG_OK; }
+    // non-null: page-locked memory the DMA engines can use directly (no staging copy)
+    virtual const uint8_t* pinned_src(const BlockRef&) { return nullptr; }
+    virtual uint8_t*       pinned_dst(const BlockRef&) { return nullptr; }
+};
+
+struct LaneStats {
+    uint64_t bytes_h2d = 0, bytes_d2h = 0, bytes_written = 0, blocks_skipped = 0, kernel_launches = 0;
+    double   ms_kernel = 0;
+};
+
+struct DeviceInfo {
+    int dev = -1;
+    int sm_count = 0;
+    std::vector<int> cpus;     // NUMA-local CPUs of the GPU (empty: no affinity)
+};
+
+class Pipe;   // defined in vmig_engine.cu
+
+// ---- process-wide context -------------------------------------------------------------------
+int  ctx_init(uint32_t gpu_mask);
+void ctx_shutdown();
+int  ctx_device_count();
+// devices selected by `mask` (0 = all initialised); error if none
+int  ctx_select(uint32_t mask, std::vector<DeviceInfo>* out);
+int  ctx_acquire_pipe(const DeviceInfo& d, Pipe** out);
+void ctx_release_pipe(Pipe* p);
+uint32_t pipe_slot_bytes();
+int  io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested, size_t lanes);
+
+// Run blocks[] through one GPU.  hashes_out[b.table_idx] receives every block's hash.
+//   hash_only : no D2H of data, no writes (block_done(b,false) is still called).
+//   err       : call-wide first-error latch shared by all lanes (0 = fine).
+int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior, bool hash_only,
+             uint32_t readers, uint32_t writers, uint64_t* hashes_out, LaneStats* stats,
+             std::atomic<int>* err, std::string* err_msg, std::mutex* err_mu);
+
+}  // namespace vmig

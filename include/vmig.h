@@ -1,0 +1,194 @@
+/*
+ * vmig.h -- C ABI of libvmig, the B200-native volume-migration engine.
+ *
+ * Drop-in boundary for the ONE data-parallel path of XShengTech/gpu-docker-api: the bulk copy
+ * of a container's system-disk diff layer (ReplicaSet Patch / Rollback / Restart) and of a
+ * Docker-volume data disk (Volume resize).  The reference has no plugin/FFI interface; the
+ * seam is three package-level Go functions in package utils:
+ *
+ *   utils.CopyDir(src, dest string) error                         reference utils/copy.go:21-27
+ *   utils.CopyOldMergedToNewContainerMerged(old, new string) error reference utils/copy.go:31-46
+ *   utils.CopyOldMountPointToContainerMountPoint(old, new) error   reference utils/copy.go:58-63
+ *     (-> moveVolumeData, reference utils/copy.go:74-128)
+ *
+ * called from internal/services/replicaset.go:333,421,831 and internal/services/volume.go:150.
+ * A cgo shim re-implements those three functions on top of the entry points
+ * below; nothing else in the reference changes.
+ *
+ * Conventions (what a cgo binding needs):
+ *   - every function returns 0 (VMIG_OK) or a negative VMIG_E* code; vmig_last_error() gives a
+ *     thread-local human-readable message for the calling thread's last failure;
+ *   - all pointers are borrowed for the duration of the call only (no Go memory is retained);
+ *   - no callbacks into the caller; every entry point is re-entrant and thread-safe (the
+ *     reference calls the copy from concurrent gin goroutines with no locking);
+ *   - there is NO CPU fallback: without a usable sm_100 device the data-path calls fail with
+ *     VMIG_ENOGPU.
+ *
+ * Data path of one migration:  source file blocks (4 MiB, file-aligned) -> pinned
+ * host slot -> cudaMemcpyAsync H2D on a side stream -> xxh64_blocks kernel (canonical XXH64,
+ * seed 0, one hash per block) -> compare with the prior version's block table -> surviving
+ * blocks cudaMemcpyAsync D2H into the destination pinned slot -> destination file.
+ */
+#ifndef VMIG_H
+#define VMIG_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMIG_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------------ */
+#define VMIG_OK          0
+#define VMIG_EINVAL     (-1)   /* bad argument (NULL path, unaligned device offset, ...)        */
+#define VMIG_ENOGPU     (-2)   /* no CUDA driver / no sm_100 device in the mask: no CPU fallback */
+#define VMIG_ECUDA      (-3)   /* a CUDA runtime call or kernel failed                          */
+#define VMIG_EIO        (-4)   /* open/read/write/metadata syscall failed, or short read/write   */
+#define VMIG_ENOMEM     (-5)   /* host or device allocation failed                              */
+#define VMIG_ETABLE     (-6)   /* malformed / incompatible block-table file                     */
+#define VMIG_EFAULT     (-7)   /* injected fault (VMIG_FAIL_BLOCK test hook)                    */
+#define VMIG_ENOTDIR    (-8)   /* src or dst is not a directory (reference utils/file.go:50-59)  */
+#define VMIG_ESRCCHANGED (-9)  /* a source file shrank while it was being read                  */
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+/* Idempotent, thread-safe.  gpu_mask bit i selects CUDA device i; 0 = all visible devices.
+ * Creates the per-GPU contexts lazily (streams, pinned staging rings, HBM slots).  Hook:
+ * reference cmd/gpu-docker-api/main.go:53-97 (Init); optional -- every call inits on demand. */
+int  vmig_init(uint32_t gpu_mask);
+/* Frees every pooled resource.  Hook: reference cmd/gpu-docker-api/main.go:139-154 (Stop). */
+void vmig_shutdown(void);
+int  vmig_device_count(void);                 /* usable sm_100 devices, or VMIG_ENOGPU          */
+const char* vmig_strerror(int code);
+const char* vmig_last_error(void);            /* thread-local detail of the last failure         */
+const char* vmig_version(void);
+
+/* ---- options / statistics ------------------------------------------------------------------ */
+#define VMIG_F_MOVE_SRC          0x01u  /* unlink source entries after a verified copy: the `mv` of
+                                           moveVolumeData (reference utils/copy.go:116)            */
+#define VMIG_F_SKIP_HIDDEN_TOPDIRS 0x02u /* reproduce `mv /root/src/*`: top-level hidden DIRECTORIES
+                                           are left behind (reference utils/copy.go:116)           */
+#define VMIG_F_MTIME_NS          0x04u  /* keep nanosecond mtimes (mv does; GNU tar's default archive
+                                           format keeps whole seconds only -> default off)         */
+#define VMIG_F_NO_METADATA       0x08u  /* data only: no chown/chmod/utimens                       */
+#define VMIG_F_HASH_ONLY         0x10u  /* build the block table of src; dst is not touched        */
+#define VMIG_F_NO_ZEROCOPY       0x20u  /* force the staged (pread/memcpy) host path               */
+
+typedef struct vmig_opts {
+    uint32_t gpu_mask;         /* 0 = every initialised GPU; blocks are sharded across the set   */
+    uint32_t block_bytes;      /* 0 -> 4 MiB (4194304); must be a multiple of 4096               */
+    uint32_t streams_per_gpu;  /* 0 -> default (4)                                               */
+    uint32_t flags;            /* VMIG_F_*                                                       */
+    uint32_t io_threads;       /* 0 -> default: host reader+writer threads per GPU               */
+    uint32_t reserved[3];
+} vmig_opts;
+
+typedef struct vmig_stats {
+    uint64_t bytes_total;      /* N: sum of regular-file sizes migrated                          */
+    uint64_t bytes_h2d;        /* bytes DMA'd host->HBM                                          */
+    uint64_t bytes_d2h;        /* bytes DMA'd HBM->host (surviving blocks)                       */
+    uint64_t bytes_written;    /* bytes written to destination files                             */
+    uint64_t blocks_total;
+    uint64_t blocks_skipped;   /* unchanged vs prior table: no D2H, no write                     */
+    uint64_t files, dirs, symlinks, hardlinks, specials;
+    uint64_t kernel_launches;  /* xxh64_blocks + diff_select launches                            */
+    uint64_t ns_total, ns_walk, ns_plan, ns_data, ns_meta, ns_table;
+    double   ms_kernel;        /* sum of CUDA-event time of the hash kernels                     */
+    uint32_t gpus_used;
+    uint32_t reserved;
+} vmig_stats;
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+/* Migrate directory tree src_dir/. into the existing directory dst_dir (semantics of
+ * `(cd src; tar c .) | (cd dst; tar x)` run as root: reference utils/copy.go:17-27 -- file
+ * bytes, mode, uid, gid, mtime, symlinks, hard links, device nodes and FIFOs are reproduced;
+ * xattrs are not; existing destination entries are overwritten, extras are never pruned).
+ *   prior_table : nullable path of the block table describing what dst ALREADY holds (the prior
+ *                 version).  Blocks whose XXH64 equals the prior entry are neither copied back
+ *                 from HBM nor written (diff-skip).
+ *   out_table   : nullable path; receives the block table of src (tmp + rename, after all data
+ *                 writes completed).
+ * Blocking; re-entrant; returns 0 or -VMIG_E*.  On error the destination may be partially
+ * written (the reference does no cleanup either: SURVEY.md §8b) but the call never reports
+ * success after a short read/write or a CUDA error. */
+int vmig_migrate_tree(const char* src_dir, const char* dst_dir,
+                      const char* prior_table, const char* out_table,
+                      const vmig_opts* opts /*nullable*/, vmig_stats* stats /*nullable*/);
+
+/* utils.CopyDir(src, dest) (reference utils/copy.go:21-27) == vmig_migrate_tree with defaults. */
+int vmig_copy_dir(const char* src_dir, const char* dst_dir);
+
+/* moveVolumeData(src, dest) on resolved host paths (reference utils/copy.go:74-128): copy then
+ * unlink the source entries, nanosecond mtimes, synchronously and with the exit status checked. */
+int vmig_move_dir(const char* src_dir, const char* dst_dir);
+
+/* Host buffer -> host buffer through the same pipeline (H2D, hash, diff, D2H of survivors).
+ * n_blocks = ceil(nbytes / block_bytes).  prior_hashes/prior_valid nullable (all blocks survive);
+ * out_hashes nullable.  dst regions of skipped blocks are left untouched.  Buffers allocated by
+ * vmig_host_alloc (or cudaHostRegister'ed by the caller) are DMA'd directly. */
+int vmig_migrate_buffer(const void* src, void* dst, uint64_t nbytes,
+                        const uint64_t* prior_hashes, const uint8_t* prior_valid,
+                        uint64_t* out_hashes, const vmig_opts* opts, vmig_stats* stats);
+int  vmig_host_alloc(void** p, uint64_t nbytes);   /* pinned host memory                        */
+void vmig_host_free(void* p);
+
+/* K1 direct: canonical XXH64(seed 0) of n blocks (host_buf + offs[i], lens[i]); the blocks are
+ * staged to HBM at 16-byte-aligned offsets and hashed by the xxh64_blocks kernel.  kernel_ms
+ * (nullable) receives the CUDA-event time of the kernel alone. */
+int vmig_hash_blocks(int gpu, const void* host_buf, const uint64_t* offs, const uint32_t* lens,
+                     uint64_t n, uint64_t* out_hashes, double* kernel_ms);
+
+/* ---- HBM-resident batch (the "block-hash GB/s" metric: inputs already in HBM) --------------- */
+typedef struct vmig_resident vmig_resident;
+/* n_blocks slots of block_bytes each in one device allocation (+ hash/prior/survivor arrays). */
+int  vmig_resident_open(int gpu, uint64_t n_blocks, uint32_t block_bytes, vmig_resident** out);
+void vmig_resident_close(vmig_resident* r);
+/* Device-side generator: 8-byte word w of block b = SplitMix64 stream `seed` at word index
+ * b*(block_bytes/8)+w (the generator of BASELINE.md §3; restated in oracle/).  All lens reset
+ * to block_bytes. */
+int  vmig_resident_fill(vmig_resident* r, uint64_t seed);
+int  vmig_resident_set_len(vmig_resident* r, uint64_t block, uint32_t len);
+int  vmig_resident_upload(vmig_resident* r, uint64_t block, const void* host, uint32_t len);
+int  vmig_resident_download(vmig_resident* r, uint64_t block, void* host, uint32_t len);
+/* XOR the first 8 bytes of each listed block with ~0 (BASELINE.md §3 config 4's mutation). */
+int  vmig_resident_flip(vmig_resident* r, const uint64_t* blocks, uint64_t n);
+/* prior table for diff_select: hashes (nullable = none valid) + per-block validity bytes. */
+int  vmig_resident_set_prior(vmig_resident* r, const uint64_t* hashes, const uint8_t* valid);
+/* One pass = xxh64_blocks over all blocks + diff_select (ordered compaction of changed block
+ * indices).  Repeats `iters` times back to back; ms_hash / ms_total are CUDA-event times of the
+ * LAST iteration's hash kernel / of all iterations together (on the launching stream). */
+int  vmig_resident_pass(vmig_resident* r, uint32_t iters, double* ms_hash_last, double* ms_total);
+int  vmig_resident_results(vmig_resident* r, uint64_t* hashes /*n_blocks, nullable*/,
+                           uint32_t* survivors /*n_blocks cap, nullable*/, uint64_t* n_survivors);
+
+/* ---- block table + host-side helpers (no GPU needed) ---------------------------------------- */
+/* Block-table file, little-endian:
+ *   char[8] "VMIGBT01"; u32 block_bytes; u32 algo (1 = XXH64 seed 0); u64 n_files; u64 n_blocks;
+ *   n_files x { u32 path_len; char path[path_len] (relative, no leading ./); u64 size;
+ *               u64 first_block } sorted bytewise by path;
+ *   u64 hashes[n_blocks].
+ * A file of `size` bytes owns ceil(size/block_bytes) consecutive hashes (0 for an empty file).
+ * Home in the reference: merges/<rs>/<rs>-<version>/ (internal/services/replicaset.go:681-704,
+ * internal/version/merge.go:16). */
+typedef struct vmig_table_info {
+    uint32_t block_bytes, algo;
+    uint64_t n_files, n_blocks, bytes_total;
+} vmig_table_info;
+int vmig_table_info_read(const char* path, vmig_table_info* out);
+/* Copies up to cap hashes of the table into out; returns VMIG_OK. */
+int vmig_table_hashes(const char* path, uint64_t* out, uint64_t cap);
+/* utils.DirSize (reference utils/file.go:13-22): sum of non-directory sizes under dir. */
+int vmig_dir_size(const char* dir, int64_t* bytes, uint64_t* n_files);
+/* utils.ToBytes (reference utils/file.go:24-48): "20GB" -> 21474836480; 1024-based; KB/MB/GB/TB. */
+int vmig_to_bytes(const char* s, int64_t* out);
+/* Deterministic synthetic tree: n_files files of file_bytes each named
+ * f%05d.bin under dir, bytes = SplitMix64 stream seeded seed ^ fnv1a64(relative path). */
+int vmig_datagen_files(const char* dir, uint64_t seed, uint32_t n_files, uint64_t file_bytes,
+                       uint32_t threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMIG_H */

@@ -1,0 +1,396 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle.
+
+Bar (spec ③): bit-exact.  Copied bytes and metadata vs the reference's literal tar / mv pipeline
+(oracle.ref_copy / ref_move = utils/copy.go:18,116), block hashes vs the pinned XXH64 oracle."""
+import json
+import os
+import shutil
+import stat
+import threading
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import make_rich_tree
+
+pytestmark = pytest.mark.gpu
+KAT = json.loads((Path(__file__).parent / "golden" / "xxh64_kat.json").read_text())
+MiB = 1 << 20
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu(vm):
+    vm.init(0)          # raises VMIG_ENOGPU loudly if the box has no B200: no fallback to test
+    yield
+    vm.shutdown()
+
+
+# ------------------------------------------------------------------------------------------ K1
+def test_k1_known_answer_vectors(vm, orc):
+    buf = np.frombuffer(orc.sanity_buffer(4 * MiB), dtype=np.uint8)
+    lens = np.array(sorted(int(n) for n in KAT["sanity"]), dtype=np.uint32)
+    offs = np.zeros(len(lens), dtype=np.uint64)          # every vector is a prefix of the buffer
+    got, _ = vm.hash_blocks(buf, offs, lens)
+    for n, h in zip(lens, got):
+        assert int(h) == int(KAT["sanity"][str(int(n))], 16), int(n)
+    z, _ = vm.hash_blocks(np.zeros(4 * MiB, np.uint8), [0], [4 * MiB])
+    assert int(z[0]) == int(KAT["zeros_4MiB"], 16)
+    for s, want in KAT["ascii"].items():
+        b = np.frombuffer(s.encode(), dtype=np.uint8)
+        g, _ = vm.hash_blocks(b, [0], [len(b)])
+        assert int(g[0]) == int(want, 16), s
+
+
+def test_k1_every_short_length_and_tail(vm, orc):
+    """lengths 0..300 (all tail shapes: 8-, 4-, 1-byte steps, no-stripe path) at odd offsets."""
+    rng = np.random.default_rng(1)
+    lens = np.arange(0, 301, dtype=np.uint32)
+    offs = np.cumsum(np.concatenate([[1], lens[:-1].astype(np.uint64) + 1])).astype(np.uint64)
+    buf = rng.integers(0, 256, int(offs[-1] + lens[-1] + 8), dtype=np.uint8)
+    got, _ = vm.hash_blocks(buf, offs, lens)
+    assert (got == orc.hash_blocks(buf, offs, lens)).all()
+
+
+def test_k1_ragged_blocks_vs_oracle(vm, orc):
+    """random lengths up to 4 MiB+; chunk (2 KiB) and stripe (32 B) boundaries +-1; > one batch."""
+    rng = np.random.default_rng(2)
+    special = [2047, 2048, 2049, 2079, 2080, 4095, 4096, 4097, 6143, 6144, 6176, 65535, 65536, 65537,
+               4 * MiB - 33, 4 * MiB - 32, 4 * MiB - 1, 4 * MiB, 4 * MiB + 1, 4 * MiB + 33, 5 * MiB + 7]
+    lens = np.array(special + list(rng.integers(0, 3 * MiB, 40)), dtype=np.uint32)
+    rng.shuffle(lens)
+    offs = np.cumsum(np.concatenate([[5], lens[:-1].astype(np.uint64) + rng.integers(0, 9, len(lens) - 1).astype(np.uint64)])).astype(np.uint64)
+    buf = rng.integers(0, 256, int(offs[-1] + lens[-1]), dtype=np.uint8)
+    got, ms = vm.hash_blocks(buf, offs, lens)
+    want = orc.hash_blocks(buf, offs, lens)
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, [(int(i), int(lens[i])) for i in bad[:10]]
+    assert ms > 0
+
+
+def test_k1_many_small_blocks_dynamic_scheduling(vm, orc):
+    """20 000 small blocks: several batches of 4096, work-stealing counter, zero-length blocks."""
+    rng = np.random.default_rng(3)
+    lens = rng.integers(0, 700, 20000).astype(np.uint32)
+    lens[::97] = 0
+    offs = np.concatenate([[0], np.cumsum(lens[:-1].astype(np.uint64))]).astype(np.uint64)
+    buf = rng.integers(0, 256, int(lens.astype(np.uint64).sum()) + 1, dtype=np.uint8)
+    got, _ = vm.hash_blocks(buf, offs, lens)
+    assert (got == orc.hash_blocks(buf, offs, lens)).all()
+
+
+def test_k1_rejects_block_larger_than_slot(vm):
+    with pytest.raises(vm.VmigError) as ei:
+        vm.hash_blocks(np.zeros(40 * MiB, np.uint8), [0], [40 * MiB])
+    assert ei.value.code == vm.VMIG_EINVAL
+
+
+# ------------------------------------------------------------------------------------ resident
+def test_resident_fill_hash_diff_select(vm, orc):
+    """HBM-resident pass: device generator == oracle generator, hashes == oracle on sampled
+    blocks, and diff_select returns exactly the flipped / invalid-prior blocks, ascending."""
+    n, bb = 300, 4 * MiB
+    r = vm.Resident(n, bb)
+    try:
+        r.fill(1234)
+        words = bb // 8
+        sample = [0, 1, 147, 148, 149, 299]
+        for b in sample:
+            dev = r.download(b, bb)
+            assert (dev == orc.splitmix_bytes(1234, bb, first_word=b * words)).all(), b
+        r.set_prior(None)
+        r.run(1)
+        h1, surv = r.results()
+        assert len(surv) == n and (surv == np.arange(n)).all()      # no prior: everything survives
+        for b in sample:
+            assert int(h1[b]) == orc.xxh64(orc.splitmix_bytes(1234, bb, first_word=b * words)), b
+        assert len(set(h1.tolist())) == n
+        # prior = these hashes; flip 30% of the blocks; two blocks have no valid prior
+        flip = np.sort(np.random.default_rng(44).permutation(n)[: n * 3 // 10]).astype(np.uint64)
+        valid = np.ones(n, np.uint8)
+        valid[[5, 250]] = 0
+        r.set_prior(h1, valid)
+        r.flip(flip)
+        ms_hash, ms_total = r.run(2)
+        h2, surv = r.results()
+        want = sorted(set(flip.tolist()) | {5, 250})
+        assert surv.tolist() == want
+        same = np.setdiff1d(np.arange(n), flip)
+        assert (h2[same] == h1[same]).all() and (h2[flip.astype(int)] != h1[flip.astype(int)]).all()
+        b = int(flip[0])
+        blk = orc.splitmix_bytes(1234, bb, first_word=b * words).copy()
+        blk[:8] ^= 0xFF
+        assert int(h2[b]) == orc.xxh64(blk)
+        assert 0 < ms_hash <= ms_total
+        # ragged lengths inside resident slots
+        for b, ln in [(0, 0), (1, 31), (2, 4 * MiB - 1), (3, 2049)]:
+            r.set_len(b, ln)
+        r.run(1)
+        h3, _ = r.results()
+        for b, ln in [(0, 0), (1, 31), (2, 4 * MiB - 1), (3, 2049)]:
+            blk = r.download(b, bb)[:ln]
+            assert int(h3[b]) == orc.xxh64(blk), (b, ln)
+    finally:
+        r.close()
+
+
+# ------------------------------------------------------------------------------------- the tree
+def test_copydir_matches_reference_tar_pipeline(vm, orc, shm_tmp):
+    """utils.CopyDir parity: same tree as `(cd src; tar c .) | (cd dst; tar x)` incl. ns-exact
+    (i.e. whole-second) mtimes, hard links, specials, replaced pre-existing entries."""
+    src, dst, ref = shm_tmp / "src", shm_tmp / "dst", shm_tmp / "ref"
+    for d in (src, dst, ref):
+        d.mkdir()
+    make_rich_tree(src, orc)
+    for d in (dst, ref):        # pre-existing destination entries
+        (d / "big.bin").write_bytes(b"old")
+        os.link(d / "big.bin", d / "keepme")
+        (d / "lnk").write_bytes(b"was a file")
+        (d / "sub").mkdir()
+        (d / "sub" / "stale").write_bytes(b"stale")
+    vm.CopyDir(str(src), str(dst))
+    assert orc.ref_copy(src, ref).returncode == 0
+    assert orc.compare_trees(ref, dst, mtime_ns=True) == []
+    assert (dst / "keepme").read_bytes() == b"old" and (dst / "sub" / "stale").exists()
+    assert orc.compare_trees(src, dst, ignore_root_mtime=True)[:0] == []      # src untouched:
+    assert (src / "big.bin").exists()
+
+
+def test_block_table_matches_oracle(vm, orc, shm_tmp):
+    src, dst = shm_tmp / "src", shm_tmp / "dst"
+    src.mkdir(), dst.mkdir()
+    make_rich_tree(src, orc)
+    st = vm.migrate_tree(src, dst, None, shm_tmp / "t.vmig")
+    entries, want = orc.block_table_of_tree(src)
+    tab = orc.read_table(shm_tmp / "t.vmig")
+    assert tab["entries"] == entries
+    assert (tab["hashes"] == want).all()
+    assert st["blocks_total"] == len(want) and st["bytes_total"] == sum(e[1] for e in entries)
+    assert st["blocks_skipped"] == 0 and st["kernel_launches"] >= 1 and st["ms_kernel"] > 0
+    # hard-linked paths are hashed once: fewer bytes cross PCIe than the table describes
+    assert st["bytes_h2d"] < st["bytes_total"] and st["bytes_d2h"] == st["bytes_h2d"] == st["bytes_written"]
+    # hash-only mode: same table, destination untouched
+    vm.hash_tree(src, shm_tmp / "t2.vmig")
+    assert (shm_tmp / "t2.vmig").read_bytes() == (shm_tmp / "t.vmig").read_bytes()
+
+
+def _mutate(path: Path, block: int, bb=4 * MiB):
+    with open(path, "r+b") as f:
+        f.seek(block * bb)
+        w = bytearray(f.read(8))
+        for i in range(len(w)):
+            w[i] ^= 0xFF
+        f.seek(block * bb)
+        f.write(w)
+
+
+def test_diff_skip_copies_exactly_the_changed_blocks(vm, orc, shm_tmp):
+    """BASELINE config 4 in miniature: dst holds the prior version + its block table; only the
+    changed blocks travel back over PCIe and get written; dst == src afterwards."""
+    src, dst = shm_tmp / "src", shm_tmp / "dst"
+    src.mkdir(), dst.mkdir()
+    sizes = {"a.bin": 24 * MiB, "b.bin": 12 * MiB + 100, "c.bin": 5 * MiB, "d/e.bin": 9 * MiB, "same.bin": 8 * MiB}
+    for name, sz in sizes.items():
+        (src / name).parent.mkdir(exist_ok=True)
+        (src / name).write_bytes(orc.splitmix_bytes(orc.file_seed(9, name), sz).tobytes())
+    vm.CopyDir(str(src), str(dst))                               # v1 in dst
+    vm.hash_tree(dst, shm_tmp / "v1.vmig")                       # the prior table
+    assert (orc.read_table(shm_tmp / "v1.vmig")["hashes"] == orc.block_table_of_tree(dst)[1]).all()
+    # v2 = src with: 3 blocks changed in a, last (short) block changed in b, c grown, e shrunk,
+    # a brand-new file, and one file deleted from dst behind the table's back
+    for blk in (0, 3, 5):
+        _mutate(src / "a.bin", blk)
+    _mutate(src / "b.bin", 3)
+    with open(src / "c.bin", "ab") as f:
+        f.write(orc.splitmix_bytes(77, 3 * MiB + 5).tobytes())
+    os.truncate(src / "d" / "e.bin", 6 * MiB + 9)
+    (src / "new.bin").write_bytes(orc.splitmix_bytes(78, 4 * MiB + 1).tobytes())
+    mtime_same = os.lstat(dst / "same.bin").st_mtime_ns
+    st = vm.migrate_tree(src, dst, shm_tmp / "v1.vmig", shm_tmp / "v2.vmig")
+    # expected survivors: a:3, b:1 (short tail block), c: block 1 (was 1 MiB, now full) + block 2 (new),
+    # e: block 1 (was full, now 2 MiB+9), new.bin: 2  -> 9; everything else skipped
+    n_blocks = sum((os.path.getsize(src / n) + 4 * MiB - 1) // (4 * MiB) for n in list(sizes) + ["new.bin"])
+    assert st["blocks_total"] == n_blocks
+    assert st["blocks_total"] - st["blocks_skipped"] == 9, st
+    changed_bytes = 3 * 4 * MiB + 100 + 4 * MiB + 5 + (2 * MiB + 9) + 4 * MiB + 1
+    assert st["bytes_d2h"] == changed_bytes == st["bytes_written"]
+    assert st["bytes_h2d"] == st["bytes_total"]
+    ref = shm_tmp / "ref"
+    ref.mkdir()
+    orc.ref_copy(src, ref)
+    assert orc.compare_trees(ref, dst, mtime_ns=True) == []
+    assert (orc.read_table(shm_tmp / "v2.vmig")["hashes"] == orc.block_table_of_tree(src)[1]).all()
+    assert os.lstat(dst / "same.bin").st_mtime_ns == mtime_same
+    # re-running against the new table moves nothing at all ("resume for free")
+    st2 = vm.migrate_tree(src, dst, shm_tmp / "v2.vmig", None)
+    assert st2["blocks_skipped"] == st2["blocks_total"] and st2["bytes_d2h"] == 0 and st2["bytes_written"] == 0
+    # a stale table entry for a file that vanished from dst is not trusted
+    os.unlink(dst / "a.bin")
+    st3 = vm.migrate_tree(src, dst, shm_tmp / "v2.vmig", None)
+    assert st3["blocks_total"] - st3["blocks_skipped"] == 6
+    assert orc.compare_trees(ref, dst, mtime_ns=True) == []
+
+
+def test_move_matches_reference_mv(vm, orc, shm_tmp, tmp_path):
+    """CopyOldMountPointToContainerMountPoint parity with the helper container's command
+    (utils/copy.go:116) run across two mounts; plus the documented divergence (hidden top dirs)."""
+    def build(root):
+        root.mkdir()
+        (root / "d").mkdir(); (root / "d" / ".inner").mkdir()
+        (root / "d" / "y.bin").write_bytes(orc.splitmix_bytes(5, 5 * MiB + 3).tobytes())
+        (root / ".dotfile").write_bytes(b"3"); (root / "plain").write_bytes(b"4" * 5000)
+        os.symlink("plain", root / "l")
+        (root / ".hid").mkdir(); (root / ".hid" / "x").write_bytes(b"1")
+        t = 1_577_934_245_123_456_789
+        for p in (root / "plain", root / "d" / "y.bin", root / "d"):
+            os.utime(p, ns=(t, t))
+    s1, s2 = shm_tmp / "s1", shm_tmp / "s2"
+    d1, d2 = tmp_path / "d1", tmp_path / "d2"
+    build(s1), build(s2), d1.mkdir(), d2.mkdir()
+    orc.ref_move(s1, d1)
+    st = vm.migrate_tree(s2, d2, flags=vm.F_MOVE_SRC | vm.F_SKIP_HIDDEN_TOPDIRS)
+    assert st["files"] == 3
+    diffs = [d for d in orc.compare_trees(d1, d2, mtime_ns=True) if not d.startswith(".:")]
+    assert diffs == [], diffs
+    assert sorted(os.listdir(s1)) == sorted(os.listdir(s2)) == [".hid"]
+    # default move (the resolver-backed reference call): hidden top-level dirs migrate too
+    s3, d3 = shm_tmp / "s3", tmp_path / "d3"
+    build(s3), d3.mkdir()
+    vm.set_resolver(None, {"vol-1": str(s3), "vol-2": str(d3)}.get)
+    vm.CopyOldMountPointToContainerMountPoint("vol-1", "vol-2")
+    vm.set_resolver(None, None)
+    assert os.listdir(s3) == [] and (d3 / ".hid" / "x").read_bytes() == b"1"
+    assert os.lstat(d3 / "plain").st_mtime_ns == 1_577_934_245_123_456_789     # mv keeps ns
+
+
+def test_container_layer_copy_through_reference_names(vm, orc, shm_tmp):
+    """CopyOldMergedToNewContainerMerged(old, new): the call PatchContainer makes
+    (services/replicaset.go:333) with the Docker inspect injected."""
+    up = {"rs-3": shm_tmp / "overlay2" / "aaa" / "diff", "rs-4": shm_tmp / "overlay2" / "bbb" / "diff"}
+    for p in up.values():
+        p.mkdir(parents=True)
+    make_rich_tree(up["rs-3"], orc, seed=21, big=5 * MiB + 1)
+    vm.set_resolver(lambda n: str(up.get(n, "")), None)
+    vm.CopyOldMergedToNewContainerMerged("rs-3", "rs-4")
+    with pytest.raises(vm.VmigError):
+        vm.CopyOldMergedToNewContainerMerged("rs-3", "rs-unknown")
+    vm.set_resolver(None, None)
+    ref = shm_tmp / "ref"
+    ref.mkdir()
+    orc.ref_copy(up["rs-3"], ref)
+    assert orc.compare_trees(ref, up["rs-4"], mtime_ns=True) == []
+
+
+def test_many_small_files_tree(vm, orc, shm_tmp):
+    """diff-layer shaped input: 3 000 files of 0..200 KiB in a depth-3 tree (groups of 64 files,
+    several batches of packed short blocks)."""
+    rng = np.random.default_rng(8)
+    src, dst, ref = shm_tmp / "src", shm_tmp / "dst", shm_tmp / "ref"
+    for d in (src, dst, ref):
+        d.mkdir()
+    for i in range(3000):
+        d = src / f"p{i % 7}" / f"q{i % 13}"
+        d.mkdir(parents=True, exist_ok=True)
+        n = int(rng.integers(0, 200 * 1024)) if i % 50 else 0
+        (d / f"f{i}.dat").write_bytes(rng.integers(0, 256, n, dtype=np.uint8).tobytes())
+    st = vm.migrate_tree(src, dst, None, shm_tmp / "t.vmig")
+    orc.ref_copy(src, ref)
+    assert orc.compare_trees(ref, dst, mtime_ns=True) == []
+    assert (orc.read_table(shm_tmp / "t.vmig")["hashes"] == orc.block_table_of_tree(src)[1]).all()
+    assert st["files"] == 3000
+
+
+def test_concurrent_calls_are_reentrant(vm, orc, shm_tmp):
+    """N gin goroutines call the copy at once with no lock (BASELINE config 5)."""
+    n = 4
+    errs = []
+    for i in range(n):
+        (shm_tmp / f"s{i}").mkdir(), (shm_tmp / f"d{i}").mkdir()
+        (shm_tmp / f"s{i}" / "x.bin").write_bytes(orc.splitmix_bytes(100 + i, 13 * MiB + i).tobytes())
+        (shm_tmp / f"s{i}" / "y.txt").write_bytes(b"y" * (i + 1))
+
+    def work(i):
+        try:
+            vm.migrate_tree(shm_tmp / f"s{i}", shm_tmp / f"d{i}", None, shm_tmp / f"t{i}.vmig")
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+    [t.start() for t in th], [t.join() for t in th]
+    assert not errs, errs
+    for i in range(n):
+        assert orc.compare_trees(shm_tmp / f"s{i}", shm_tmp / f"d{i}", ignore_root_mtime=True) == []
+        assert (orc.read_table(shm_tmp / f"t{i}.vmig")["hashes"] == orc.block_table_of_tree(shm_tmp / f"s{i}")[1]).all()
+
+
+def test_injected_fault_is_reported_not_swallowed(vm, orc, shm_tmp, monkeypatch):
+    """The reference ignores a failed copy; the engine must not."""
+    src, dst = shm_tmp / "src", shm_tmp / "dst"
+    src.mkdir(), dst.mkdir()
+    (src / "x.bin").write_bytes(orc.splitmix_bytes(1, 20 * MiB).tobytes())
+    monkeypatch.setenv("VMIG_FAIL_BLOCK", "3")
+    with pytest.raises(vm.VmigError) as ei:
+        vm.migrate_tree(src, dst, None, shm_tmp / "t.vmig")
+    assert ei.value.code == vm.VMIG_EFAULT
+    assert not (shm_tmp / "t.vmig").exists()          # no table for a failed migration
+    monkeypatch.delenv("VMIG_FAIL_BLOCK")
+    vm.CopyDir(str(src), str(dst))                    # and the engine is still usable afterwards
+    assert (dst / "x.bin").read_bytes() == (src / "x.bin").read_bytes()
+
+
+def test_missing_prior_table_is_an_error(vm, shm_tmp):
+    (shm_tmp / "s").mkdir(), (shm_tmp / "d").mkdir()
+    (shm_tmp / "s" / "f").write_bytes(b"1" * 100)
+    with pytest.raises(vm.VmigError) as ei:
+        vm.migrate_tree(shm_tmp / "s", shm_tmp / "d", shm_tmp / "nope.vmig")
+    assert ei.value.code == vm.VMIG_ETABLE
+    assert os.listdir(shm_tmp / "d") == []
+
+
+# ----------------------------------------------------------------------------------- buffers
+@pytest.mark.parametrize("pinned", [False, True])
+def test_migrate_buffer_roundtrip_and_diff(vm, orc, pinned):
+    n = 37 * MiB + 4321
+    data = orc.splitmix_bytes(31, n)
+    if pinned:
+        a, b = vm.PinnedBuffer(n), vm.PinnedBuffer(n)
+        src, dst = a.array, b.array
+    else:
+        src, dst = np.empty(n, np.uint8), np.empty(n, np.uint8)
+    src[:] = data
+    dst[:] = 0
+    h, st = vm.migrate_buffer(src, dst)
+    assert (dst == data).all()
+    nb = (n + 4 * MiB - 1) // (4 * MiB)
+    want = orc.hash_blocks(data, np.arange(nb, dtype=np.uint64) * (4 * MiB),
+                           [min(4 * MiB, n - i * 4 * MiB) for i in range(nb)])
+    assert (h == want).all()
+    assert st["bytes_h2d"] == n == st["bytes_d2h"]
+    # diff: change two blocks of src, poison dst's other blocks, migrate against the prior hashes
+    src[5 * 4 * MiB + 17] ^= 1
+    src[-1] ^= 0x80
+    dst2 = dst.copy() if not pinned else dst
+    h2, st2 = vm.migrate_buffer(src, dst2, h, np.ones(nb, np.uint8))
+    assert st2["blocks_skipped"] == nb - 2 and st2["bytes_d2h"] == 4 * MiB + (n - (nb - 1) * 4 * MiB)
+    assert (dst2 == src).all()
+    assert (np.nonzero(h2 != h)[0] == [5, nb - 1]).all()
+    if pinned:
+        a.free(), b.free()
+
+
+def test_multi_gpu_sharding_same_result(vm, orc, shm_tmp):
+    if vm.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    src, d1, d2 = shm_tmp / "src", shm_tmp / "d1", shm_tmp / "d2"
+    src.mkdir(), d1.mkdir(), d2.mkdir()
+    for i in range(6):
+        (src / f"f{i}.bin").write_bytes(orc.splitmix_bytes(60 + i, 11 * MiB + i).tobytes())
+    s1 = vm.migrate_tree(src, d1, None, shm_tmp / "t1", gpu_mask=0b01)
+    s2 = vm.migrate_tree(src, d2, None, shm_tmp / "t2", gpu_mask=0b11)
+    assert s1["gpus_used"] == 1 and s2["gpus_used"] == 2
+    assert (shm_tmp / "t1").read_bytes() == (shm_tmp / "t2").read_bytes()
+    assert orc.compare_trees(d1, d2, mtime_ns=True) == []
+
+
+def test_smoke_entry_point():
+    import __graft_entry__ as g
+    g.smoke()

@@ -1,0 +1,154 @@
+"""CPU: the C-ABI library loads, exports every symbol include/vmig.h declares, its host-side
+helpers agree with the oracle / the reference's Go helpers, and the data path FAILS LOUDLY
+without a GPU (no CPU fallback).  No compute is done here."""
+import ctypes
+import os
+import re
+import struct
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _no_gpu(vm):
+    try:
+        vm.device_count()
+        return False
+    except vm.VmigError:
+        return True
+
+
+def test_library_exports_every_declared_symbol(vm):
+    header = (ROOT / "include" / "vmig.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(vmig_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(str(vm.LIB_PATH))
+    missing = [n for n in declared if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sorted(vm.EXPORTS) == declared
+    assert "sm_100a" in vm.version()
+
+
+def test_struct_layouts_match_header(vm):
+    assert ctypes.sizeof(vm.Opts) == 32
+    assert ctypes.sizeof(vm.Stats) == 18 * 8 + 8 + 8
+    assert ctypes.sizeof(vm.TableInfo) == 32
+
+
+def test_strerror_table(vm):
+    assert vm.strerror(0) == "ok"
+    assert "no CPU fallback" in vm.strerror(vm.VMIG_ENOGPU)
+    assert vm.strerror(-12345).startswith("unknown")
+
+
+def test_to_bytes_matches_reference_rules(vm):
+    # reference utils/file.go:24-48: 1024-based, unit = last two chars, ParseFloat on the rest
+    assert vm.ToBytes("20GB") == 20 << 30
+    assert vm.ToBytes("1.5MB") == int(1.5 * (1 << 20))
+    assert vm.ToBytes("100KB") == 100 << 10 and vm.ToBytes("2TB") == 2 << 40
+    for bad in ["20gb", "GB", "12", "1PB", "x1GB"]:
+        with pytest.raises(vm.VmigError):
+            vm.ToBytes(bad)
+
+
+def test_dir_size_matches_walk(vm, shm_tmp):
+    (shm_tmp / "a" / "b").mkdir(parents=True)
+    (shm_tmp / "a" / "f1").write_bytes(b"x" * 1000)
+    (shm_tmp / "a" / "b" / "f2").write_bytes(b"y" * 4097)
+    os.symlink("f1", shm_tmp / "a" / "l")
+    want = sum(os.lstat(os.path.join(d, f)).st_size for d, _, fs in os.walk(shm_tmp) for f in fs)
+    assert vm.DirSize(str(shm_tmp)) == want
+    with pytest.raises(vm.VmigError):
+        vm.DirSize(str(shm_tmp / "nope"))
+
+
+def test_datagen_matches_oracle_generator(vm, orc, shm_tmp):
+    vm.datagen_files(shm_tmp / "g", 7, 3, (4 << 20) + 12345, threads=4)
+    for i in range(3):
+        name = f"f{i:05d}.bin"
+        got = np.fromfile(shm_tmp / "g" / name, dtype=np.uint8)
+        want = orc.splitmix_bytes(orc.file_seed(7, name), (4 << 20) + 12345)
+        assert got.size == want.size and (got == want).all(), name
+
+
+def _write_table(path, entries, hashes, block_bytes=4 << 20):
+    raw = b"VMIGBT01" + struct.pack("<IIQQ", block_bytes, 1, len(entries), len(hashes))
+    for rel, size, first in entries:
+        raw += struct.pack("<I", len(rel)) + rel + struct.pack("<QQ", size, first)
+    raw += np.asarray(hashes, dtype="<u8").tobytes()
+    Path(path).write_bytes(raw)
+    return raw
+
+
+def test_block_table_reader_accepts_good_and_rejects_bad(vm, orc, shm_tmp):
+    entries = [(b"a/x.bin", (8 << 20) + 1, 0), (b"b.bin", 100, 3), (b"empty", 0, 4)]
+    hashes = [11, 22, 33, 44]
+    p = shm_tmp / "t.vmig"
+    raw = _write_table(p, entries, hashes)
+    info = vm.table_info(p)
+    assert info == {"block_bytes": 4 << 20, "algo": 1, "n_files": 3, "n_blocks": 4, "bytes_total": (8 << 20) + 101}
+    assert list(vm.table_hashes(p)) == hashes
+    assert orc.read_table(p)["entries"] == entries              # the oracle's parser agrees on the format
+    for bad in [raw[:-1], b"XMIGBT01" + raw[8:], raw[:40], raw + b"\0" * 8]:
+        (shm_tmp / "bad").write_bytes(bad)
+        with pytest.raises(vm.VmigError) as ei:
+            vm.table_info(shm_tmp / "bad")
+        assert ei.value.code == vm.VMIG_ETABLE
+    _write_table(shm_tmp / "unsorted", [(b"b", 1, 0), (b"a", 1, 1)], [1, 2])
+    with pytest.raises(vm.VmigError):
+        vm.table_info(shm_tmp / "unsorted")
+    _write_table(shm_tmp / "gap", [(b"a", 1, 0), (b"b", 1, 2)], [1, 2, 3])
+    with pytest.raises(vm.VmigError):
+        vm.table_info(shm_tmp / "gap")
+
+
+def test_reference_interface_resolvers(vm):
+    vm.set_resolver(None, None)
+    with pytest.raises(vm.VmigError):
+        vm.GetContainerMergedLayer("rs-1")
+    vm.set_resolver(lambda n: "" if n == "missing" else f"/var/lib/docker/overlay2/{n}/diff", lambda n: f"/vol/{n}/_data")
+    assert vm.GetContainerMergedLayer("rs-2") == "/var/lib/docker/overlay2/rs-2/diff"
+    assert vm.GetVolumeMountPoint("v-1") == "/vol/v-1/_data"
+    with pytest.raises(vm.VmigError):           # empty UpperDir is an error (utils/copy.go:50-52)
+        vm.GetContainerMergedLayer("missing")
+    vm.set_resolver(None, None)
+
+
+def test_argument_validation_needs_no_gpu(vm, shm_tmp):
+    with pytest.raises(vm.VmigError) as ei:
+        vm.migrate_tree(None, shm_tmp)
+    assert ei.value.code == vm.VMIG_EINVAL
+    with pytest.raises(vm.VmigError) as ei:
+        vm.migrate_tree(shm_tmp / "nope", shm_tmp)
+    assert ei.value.code == vm.VMIG_EIO
+    (shm_tmp / "file").write_bytes(b"1")
+    with pytest.raises(vm.VmigError) as ei:
+        vm.migrate_tree(shm_tmp / "file", shm_tmp)
+    assert ei.value.code == vm.VMIG_ENOTDIR
+    with pytest.raises(vm.VmigError) as ei:
+        vm.migrate_tree(shm_tmp, shm_tmp, block_bytes=1000)
+    assert ei.value.code == vm.VMIG_EINVAL
+
+
+def test_no_cpu_fallback_without_gpu(vm, shm_tmp):
+    """On a GPU-less box every data-path call must fail with VMIG_ENOGPU and leave dst alone."""
+    if not _no_gpu(vm):
+        pytest.skip("a GPU is present; the -m gpu tests cover the data path")
+    src, dst = shm_tmp / "s", shm_tmp / "d"
+    src.mkdir(), dst.mkdir()
+    (src / "f").write_bytes(b"payload")
+    for call in (lambda: vm.CopyDir(str(src), str(dst)),
+                 lambda: vm.migrate_tree(src, dst),
+                 lambda: vm.hash_blocks(np.zeros(64, np.uint8), [0], [64]),
+                 lambda: vm.migrate_buffer(np.zeros(4096, np.uint8), np.zeros(4096, np.uint8)),
+                 lambda: vm.Resident(4),
+                 lambda: vm.init(0)):
+        with pytest.raises(vm.VmigError) as ei:
+            call()
+        assert ei.value.code == vm.VMIG_ENOGPU, ei.value
+    assert os.listdir(dst) == []
+    assert (src / "f").exists()
