@@ -303,6 +303,7 @@ struct Batch {
     std::atomic<int> reads_left{0}, writes_left{0};
     bool failed = false;
     std::vector<uint8_t> survive;   // per block, filled after hashing
+    uint64_t t_disp = 0, t_read = 0, t_sub = 0, t_hash = 0, t_d2h = 0, t_done = 0;   // VMIG_TRACE
 };
 struct IoTask { Batch* batch; size_t i0, i1; };
 
@@ -336,7 +337,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
             b->b0 = i; size_t used = 0;
             while (i < blocks.size() && (i - b->b0) < kMaxBatchBlocks) {
                 const size_t need = align_up(std::max<uint32_t>(blocks[i].len, 1), kBlockAlign);
-                if (need > slot_bytes) { set_last_error("block of %u bytes exceeds the %u-byte staging slot (VMIG_SLOT_MB)", blocks[i].len, slot_bytes); return VMIG_EINVAL; }
+                if (need > slot_bytes) { set_last_error("block of %u bytes exceeds the %u-byte staging slot (VMIG_SLOT_MB)", blocks[i].len, slot_bytes); set_err(VMIG_EINVAL); return VMIG_EINVAL; }
                 if (used + need > slot_bytes) break;
                 slot_off[i] = (uint32_t)used; used += need; i++;
             }
@@ -353,7 +354,10 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
     std::mutex done_mu; std::condition_variable done_cv; size_t batches_done = 0;
     std::mutex stat_mu;
 
+    std::atomic<uint64_t> rd_busy{0}, wr_busy{0}, slot_wait{0};
+    const uint64_t lane_t0 = now_ns();
     auto finish_batch = [&](Batch* b) {
+        b->t_done = now_ns();
         free_slots.push(b->slot);
         std::lock_guard<std::mutex> lk(done_mu);
         if (++batches_done == n_batches) done_cv.notify_all();
@@ -367,8 +371,9 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
         for (auto& bp : batches) {
             Batch* b = bp.get();
             int s;
+            const uint64_t w0 = now_ns();
             if (!free_slots.pop(&s)) return;
-            b->slot = s;
+            b->slot = s; b->t_disp = now_ns(); slot_wait += b->t_disp - w0;
             if (direct_src || err->load()) { b->failed = err->load() != 0; submit_q.push(b); continue; }
             // group small blocks so a task carries >= 1 MiB or 64 blocks
             std::vector<IoTask> tasks;
@@ -391,12 +396,14 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
             IoTask k;
             while (read_q.pop(&k)) {
                 Slot& sl = pipe->slots[k.batch->slot];
+                const uint64_t r0 = now_ns();
                 if (!err->load())
                     for (size_t i = k.i0; i < k.i1; i++) {
                         int rc = io->read_block(blocks[i], sl.h_in + slot_off[i]);
                         if (rc) { set_err(rc); break; }
                     }
-                if (k.batch->reads_left.fetch_sub(1) == 1) submit_q.push(k.batch);
+                rd_busy += now_ns() - r0;
+                if (k.batch->reads_left.fetch_sub(1) == 1) { k.batch->t_read = now_ns(); submit_q.push(k.batch); }
             }
         });
 
@@ -461,6 +468,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
         while (submit_q.pop(&b)) {
             if (err->load()) b->failed = true;
             if (!b->failed) { int rc = submit_one(b); if (rc) { set_err(rc); b->failed = true; } }
+            b->t_sub = now_ns();
             hashwait_q.push(b);
         }
     });
@@ -508,6 +516,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
             if (err->load()) b->failed = true;
             if (!b->failed) { int rc = after_hash(b); if (rc) { set_err(rc); b->failed = true; } }
             if (b->failed) b->survive.assign(b->b1 - b->b0, 0);
+            b->t_hash = now_ns();
             d2hwait_q.push(b);
         }
     });
@@ -524,6 +533,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
                 if (e != cudaSuccess) { fail(VMIG_ECUDA, "cudaEventSynchronize(d2h): %s", cudaGetErrorString(e)); set_err(VMIG_ECUDA); b->failed = true; }
             }
             const size_t n = b->b1 - b->b0;
+            b->t_d2h = now_ns();
             std::vector<IoTask> tasks;
             if (!b->failed && !hash_only && !direct_dst) {
                 size_t i = 0;
@@ -560,12 +570,14 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
             while (write_q.pop(&k)) {
                 Slot& sl = pipe->slots[k.batch->slot];
                 uint64_t wrote = 0;
+                const uint64_t w0 = now_ns();
                 for (size_t i = k.i0; i < k.i1; i++) {
                     if (err->load()) break;
                     int rc = io->write_block(blocks[i], sl.h_out + slot_off[i]);
                     if (!rc) { wrote += blocks[i].len; rc = io->block_done(blocks[i], true); }
                     if (rc) { set_err(rc); break; }
                 }
+                wr_busy += now_ns() - w0;
                 { std::lock_guard<std::mutex> lk(stat_mu); stats->bytes_written += wrote; }
                 if (k.batch->writes_left.fetch_sub(1) == 1) finish_batch(k.batch);
             }
@@ -580,6 +592,21 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
     for (auto& t : readers) t.join();
     submitter.join(); hashwaiter.join(); d2hwaiter.join();
     for (auto& t : writers) t.join();
+    if (env_long("VMIG_TRACE", 0)) {
+        const double wall = (now_ns() - lane_t0) / 1e6;
+        double a[5] = {0, 0, 0, 0, 0}; size_t nb = 0;
+        for (auto& bp : batches) {
+            const Batch& b = *bp;
+            if (!b.t_done || !b.t_disp) continue;
+            a[0] += (b.t_read ? b.t_read - b.t_disp : 0) / 1e6; a[1] += (b.t_sub - std::max(b.t_read, b.t_disp)) / 1e6;
+            a[2] += (b.t_hash - b.t_sub) / 1e6; a[3] += (b.t_d2h - b.t_hash) / 1e6; a[4] += (b.t_done - b.t_d2h) / 1e6; nb++;
+        }
+        fprintf(stderr, "[vmig trace] gpu %d: %zu batches in %.1f ms; mean ms/batch: read %.2f submit-wait %.2f h2d+hash %.2f d2h %.2f write %.2f; "
+                        "reader busy %.0f%% of %u, writer busy %.0f%% of %u; dispatcher waited %.1f ms for slots; kernel sum %.1f ms\n",
+                pipe->dev.dev, nb, wall, a[0] / nb, a[1] / nb, a[2] / nb, a[3] / nb, a[4] / nb,
+                100.0 * rd_busy.load() / 1e6 / (wall * n_readers), n_readers, 100.0 * wr_busy.load() / 1e6 / (wall * n_writers), n_writers,
+                slot_wait.load() / 1e6, stats->ms_kernel);
+    }
     // the slots go back to the pool idle
     cudaSetDevice(pipe->dev.dev);
     for (auto& s : pipe->slots) cudaStreamSynchronize(s.stream);

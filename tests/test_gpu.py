@@ -148,6 +148,8 @@ def test_copydir_matches_reference_tar_pipeline(vm, orc, shm_tmp):
         (d / "lnk").write_bytes(b"was a file")
         (d / "sub").mkdir()
         (d / "sub" / "stale").write_bytes(b"stale")
+        for p in (d / "keepme", d / "sub" / "stale"):          # entries outside src keep their own times
+            os.utime(p, ns=(10**18, 10**18 + 7))
     vm.CopyDir(str(src), str(dst))
     assert orc.ref_copy(src, ref).returncode == 0
     assert orc.compare_trees(ref, dst, mtime_ns=True) == []
@@ -242,8 +244,9 @@ def test_move_matches_reference_mv(vm, orc, shm_tmp, tmp_path):
         os.symlink("plain", root / "l")
         (root / ".hid").mkdir(); (root / ".hid" / "x").write_bytes(b"1")
         t = 1_577_934_245_123_456_789
-        for p in (root / "plain", root / "d" / "y.bin", root / "d"):
-            os.utime(p, ns=(t, t))
+        for dp, dn, fn in os.walk(root, topdown=False):      # identical times in every copy of the tree
+            for n in fn + dn:
+                os.utime(os.path.join(dp, n), ns=(t, t + len(n)), follow_symlinks=False)
     s1, s2 = shm_tmp / "s1", shm_tmp / "s2"
     d1, d2 = tmp_path / "d1", tmp_path / "d2"
     build(s1), build(s2), d1.mkdir(), d2.mkdir()
@@ -260,7 +263,7 @@ def test_move_matches_reference_mv(vm, orc, shm_tmp, tmp_path):
     vm.CopyOldMountPointToContainerMountPoint("vol-1", "vol-2")
     vm.set_resolver(None, None)
     assert os.listdir(s3) == [] and (d3 / ".hid" / "x").read_bytes() == b"1"
-    assert os.lstat(d3 / "plain").st_mtime_ns == 1_577_934_245_123_456_789     # mv keeps ns
+    assert os.lstat(d3 / "plain").st_mtime_ns == 1_577_934_245_123_456_789 + 5     # mv keeps ns
 
 
 def test_container_layer_copy_through_reference_names(vm, orc, shm_tmp):
