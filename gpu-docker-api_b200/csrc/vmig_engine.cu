@@ -81,10 +81,25 @@ public:
     uint32_t slot_bytes = 0;
     std::vector<Slot> slots;
     int create(const DeviceInfo& d);
+    int create_here(const DeviceInfo& d);
     void destroy();
 };
 
+static void bind_thread(const DeviceInfo& d);
+
+// The pinned rings are allocated and first-touched by a thread bound to the GPU's NUMA-local
+// CPUs, so that staging copies and both DMA directions stay on the GPU's socket (on the 2-socket
+// bench box a ring on the far socket sends every byte across UPI four times).
 int Pipe::create(const DeviceInfo& d)
+{
+    int rc = VMIG_OK; std::string msg;
+    std::thread t([&] { bind_thread(d); rc = create_here(d); if (rc) msg = last_error_cstr(); });
+    t.join();
+    if (rc) set_last_error_str(msg);
+    return rc;
+}
+
+int Pipe::create_here(const DeviceInfo& d)
 {
     load_tunables();
     dev = d; slot_bytes = g_slot_bytes;
@@ -321,6 +336,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
     if (blocks.empty()) return VMIG_OK;
     const uint32_t slot_bytes = pipe->slot_bytes;
     const long fail_block = env_long("VMIG_FAIL_BLOCK", -1);
+    const bool bind_io = env_long("VMIG_BIND_IO", 1) != 0;      // reader/writer threads on the GPU's socket
 
     auto set_err = [&](int code) {
         int expect = 0;
@@ -349,7 +365,11 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
 
     BQ<int> free_slots;
     for (int s = 0; s < (int)pipe->slots.size(); s++) free_slots.push(s);
-    BQ<IoTask> read_q, write_q;
+    BQ<IoTask> read_q;
+    // one queue per writer, keyed by destination file: a file accepts writes from one thread at
+    // a time anyway (inode lock), so two writers on one file only queue up behind each other
+    std::vector<std::unique_ptr<BQ<IoTask>>> write_qs;
+    for (uint32_t t = 0; t < n_writers; t++) write_qs.push_back(std::make_unique<BQ<IoTask>>());
     BQ<Batch*> submit_q, hashwait_q, d2hwait_q;
     std::mutex done_mu; std::condition_variable done_cv; size_t batches_done = 0;
     std::mutex stat_mu;
@@ -392,7 +412,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
     std::vector<std::thread> readers;
     for (uint32_t t = 0; t < n_readers; t++)
         readers.emplace_back([&] {
-            bind_thread(pipe->dev);
+            if (bind_io) bind_thread(pipe->dev);
             IoTask k;
             while (read_q.pop(&k)) {
                 Slot& sl = pipe->slots[k.batch->slot];
@@ -557,17 +577,17 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
             }
             if (tasks.empty()) { finish_batch(b); continue; }
             b->writes_left.store((int)tasks.size());
-            for (auto& t : tasks) write_q.push(t);
+            for (auto& t : tasks) write_qs[blocks[t.i0].file % n_writers]->push(t);
         }
     });
 
     // ---- stage 6: writers
     std::vector<std::thread> writers;
     for (uint32_t t = 0; t < n_writers; t++)
-        writers.emplace_back([&] {
-            bind_thread(pipe->dev);
+        writers.emplace_back([&, t] {
+            if (bind_io) bind_thread(pipe->dev);
             IoTask k;
-            while (write_q.pop(&k)) {
+            while (write_qs[t]->pop(&k)) {
                 Slot& sl = pipe->slots[k.batch->slot];
                 uint64_t wrote = 0;
                 const uint64_t w0 = now_ns();
@@ -587,7 +607,8 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
         std::unique_lock<std::mutex> lk(done_mu);
         done_cv.wait(lk, [&] { return batches_done == n_batches; });
     }
-    read_q.close(); submit_q.close(); hashwait_q.close(); d2hwait_q.close(); write_q.close(); free_slots.close();
+    read_q.close(); submit_q.close(); hashwait_q.close(); d2hwait_q.close(); free_slots.close();
+    for (auto& q : write_qs) q->close();
     dispatcher.join();
     for (auto& t : readers) t.join();
     submitter.join(); hashwaiter.join(); d2hwaiter.join();

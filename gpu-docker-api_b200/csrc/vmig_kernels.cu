@@ -7,22 +7,33 @@
 //                    SURVEY.md Appendix A and checked bit-for-bit against oracle/xxh64_ref.c.
 // K2  diff_select  : ordered compaction of the changed flags into a survivor index list.
 //
-// Why K1 looks the way it does:
-//  * XXH64 is four dependent chains per block (acc = rotl(acc + x*P2, 31) * P1 per 8 input
-//    bytes per chain; rotl breaks associativity) so the only parallelism inside a block is 4.
+// Why K1 looks the way it does (measurements in profiles/r01_chain_probe.txt):
+//  * XXH64 is four dependent chains per block (acc = rotl(acc + x*P2, 31) * P1 per 8 input bytes
+//    per chain; rotl breaks associativity) so the only parallelism inside a block is 4.
 //    Parallelism comes from hashing many blocks at once: one QUAD (4 lanes) per block, 8 blocks
-//    per warp, kWarps warps per CTA, one persistent CTA per SM.
-//  * Each lane walks an 8-byte column with a 32-byte stride -- poison for global loads -- so the
-//    bytes are staged through shared memory by the TMA engine: one elected lane per quad issues
-//    1-D bulk copies (cp.async.bulk global->shared, SASS UBLKCP) of kChunk contiguous bytes of
-//    its block into a kStages-deep ring and the quad consumes them with conflict-free LDS.64
-//    (quad slots are padded by 32 B so the 4 quads of a half-warp hit disjoint bank groups).
-//    Completion is tracked by one mbarrier per (warp, stage); no CTA-wide barrier is used in
-//    the steady state and no LSU bandwidth is spent on the copy.
+//    per consumer warp, 4 consumer warps per CTA (one per SM sub-partition), one persistent CTA
+//    per SM -> 32 blocks in flight per SM.
+//  * With ~17 blocks per SM at the 10 GiB bench size the kernel is bound by the LATENCY of that
+//    chain, so the chain is what is engineered.  On B200 IMAD/IADD3/SHF have 4.4-cycle dependent
+//    latency but IMAD.WIDE / IMAD.HI (the 32x32->64 product a 64-bit multiply needs) take ~12.5
+//    cycles and occupy their unit ~7 cycles.  A round needs two 64-bit multiplies (x*P2 and
+//    rotl(..)*P1); only the second depends on the chain.  So the work is split by warp role:
+//      - PRODUCER warps (one per consumer warp) pull block indices from a global atomic counter,
+//        issue 1-D TMA bulk copies (cp.async.bulk global->shared, SASS UBLKCP) of 2 KiB chunks of
+//        each block into a 3-stage shared-memory ring, and when a chunk has landed PRE-MULTIPLY
+//        it in place (x -> x*P2, LDS.128/STS.128, fully parallel, off every chain);
+//      - CONSUMER warps run the chains: per 8 bytes one LDS.64, two funnel shifts, two IMADs
+//        and ONE IMAD.WIDE whose 64-bit addend carries x*P2 -- a 24-cycle round
+//        (nvcc's own lowering of the 64-bit expression: 42 cycles).
+//    The three hand-offs per stage (TMA landed / pre-multiplied / drained) are mbarriers; the
+//    steady state has no CTA-wide barrier.
+//  * Each chain lane walks an 8-byte column with a 32-byte stride; staging through shared memory
+//    turns that into contiguous 2 KiB HBM reads and conflict-free LDS.64 (quad slots are padded
+//    by 32 B so the 4 quads of a half-warp hit disjoint bank groups).
 //  * No tensor cores: there is no contraction here, only 64-bit integer mul/add/rotate.
-//  * Work distribution: quad (cta c, warp w, quad q) starts on block c + G*(w + kWarps*q) so a
-//    small batch spreads over all SMs first, then over the 4 SM sub-partitions; afterwards
-//    quads pull block indices from a global atomic counter (ragged block lengths balance).
+//  * Work distribution: quad (cta c, warp w, quad q) starts on block c + G*(w + 4*q) so a small
+//    batch spreads over all SMs first, then over the 4 sub-partitions; afterwards quads pull
+//    indices from the atomic counter (ragged block lengths balance).
 #include "vmig_kernels.cuh"
 
 namespace vmig {
@@ -35,59 +46,77 @@ constexpr uint64_t P3 = 0x165667B19E3779F9ULL;
 constexpr uint64_t P4 = 0x85EBCA77C2B2AE63ULL;
 constexpr uint64_t P5 = 0x27D4EB2F165667C5ULL;
 
-constexpr int kWarps  = 4;      // one per SM sub-partition
+constexpr int kWarps  = 4;      // consumer warps, one per SM sub-partition (+ as many producer warps)
 constexpr int kQuads  = 8;      // blocks in flight per warp
-constexpr int kChunk  = 2048;   // bytes per bulk copy (64 stripes)
-constexpr int kStages = 3;      // ring depth per quad
+constexpr int kChunk  = 1024;   // bytes per bulk copy (32 stripes)
+constexpr int kStages = 6;      // ring depth per quad: 1 draining, 1 pre-multiplied, 4 in flight from HBM
 constexpr int kQuadStride  = kChunk + 32;              // +32 B: bank-group skew between quads
 constexpr int kStageStride = kQuads * kQuadStride;
 constexpr int kWarpData    = kStages * kStageStride;
 constexpr int kWarpDesc    = kStages * kQuads * 16;     // uint4 chunk descriptors
-constexpr int kWarpBars    = kStages * 8;               // mbarriers
+constexpr int kWarpBars    = kStages * 8 + 16;          // mbarriers full[stage] + the ready / drained counters
 constexpr int kWarpSmem    = kWarpData + kWarpDesc + ((kWarpBars + 15) & ~15);
 constexpr int kSmemBytes   = kWarps * kWarpSmem;
 static_assert(kChunk % 256 == 0, "chunk must be a multiple of 8 stripes");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 constexpr uint32_t kFlagFirst = 1u, kFlagLast = 2u, kFlagNone = 4u;
+// stage-wide bits, replicated by the TMA warp into all 8 descriptors of a stage so that the chain
+// warp can branch on them without a vote: kFlagSlow = some quad has a ragged or last chunk,
+// kFlagEnd = every quad is out of work (the ring shuts down on this stage)
+constexpr uint32_t kFlagSlow = 8u, kFlagEnd = 16u;
+
+// Timeline instrumentation for probe/k1_trace.cu only (compiled out of libvmig).
+#ifdef VMIG_K1_TRACE
+__device__ long long* g_k1_trace;      // [3 roles][kTraceChunks][8] clock64 stamps of CTA 0, ring 0
+constexpr int kTraceChunks = 256;
+#define K1_TRACE_INIT long long* const k1_trace_p = (blockIdx.x == 0 && warp == 0 && lane == 0) ? g_k1_trace : nullptr
+#define K1_TRACE(role_, it_, slot_)                                                                  \
+    do {                                                                                             \
+        if (k1_trace_p && (it_) < (uint32_t)kTraceChunks)                                             \
+            k1_trace_p[((role_) * kTraceChunks + (it_)) * 8 + (slot_)] = clock64();                   \
+    } while (0)
+#else
+#define K1_TRACE_INIT do { } while (0)
+#define K1_TRACE(role_, it_, slot_) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
 __device__ __forceinline__ uint64_t xround(uint64_t acc, uint64_t x) { return rotl64(acc + x * P2, 31) * P1; }
 __device__ __forceinline__ uint64_t xmerge(uint64_t h, uint64_t v) { return (h ^ xround(0, v)) * P1 + P4; }
 
 
-// The XXH64 round acc' = rotl(acc + x*P2, 31) * P1 arranged as a 4-level dependent chain
-// (nvcc's own lowering of the 64-bit expression is 7 levels deep: it emulates the rotate with
-// SHF+SHF+LOP3 and completes the 64-bit product before the next add).
-// Carried state: acc = w + (v << 32) with w = r.lo*P1.lo (64-bit) and v = r.lo*P1.hi + r.hi*P1.lo
-// (the cross terms, only needed in the high word).  One round with input word x:
-//   t    = x.lo * P2.lo + w                 IMAD.WIDE.U32 (64-bit addend = previous wide)  level 1
-//   t.hi = t.hi + v + (x.lo*P2.hi + x.hi*P2.lo)   IADD3; the x terms are off the chain     level 2
-//   r    = rotl(t, 31)                      2 x SHF.L.W (funnel shifts)                     level 3
-//   w'   = r.lo * P1.lo                     IMAD.WIDE.U32                                   level 4
-//   v'   = r.lo*P1.hi + r.hi*P1.lo          2 x IMAD, consumed only at level 2 of the next round
+// The XXH64 round on pre-multiplied input m = x*P2 (see the header comment).
+// Carried state is t = acc + m (pre-rotation).  One step, given the NEXT pre-multiplied word:
+//   r       = rotl(t, 31)                          2 x SHF.L.W (funnel shifts)
+//   mhv     = m.hi + r.hi*P1.lo + r.lo*P1.hi       2 x IMAD (cross terms; high word only)
+//   t'      = r.lo*P1.lo + {m.lo, mhv}             1 x IMAD.WIDE.U32 with 64-bit addend
+// Written as mul.lo/mul.hi + add.cc/addc, which ptxas fuses into exactly that IMAD.WIDE
+// (23.9 cycles/round measured; every other spelling tried made ptxas split the addend off into
+// an IADD3/IADD3.X carry chain or serialise two IMAD.WIDEs: profiles/r01_chain_probe.txt).
 struct Chain {
-    uint64_t w; uint32_t v;
+    uint32_t tlo, thi;
     static constexpr uint32_t P1lo = (uint32_t)P1, P1hi = (uint32_t)(P1 >> 32);
-    static constexpr uint32_t P2lo = (uint32_t)P2, P2hi = (uint32_t)(P2 >> 32);
-    __device__ __forceinline__ void begin(uint64_t acc) { w = acc; v = 0; }
-    // Written in PTX so that neither NVVM nor ptxas re-associates the sums into a serial IMAD
-    // chain (both minimise instruction count, which here lengthens the dependent chain).
-    __device__ __forceinline__ void step(uint64_t x) {
-        uint32_t xl, xh, mh, tlo, thi, rl, rh;
-        asm("mov.b64 {%0, %1}, %2;" : "=r"(xl), "=r"(xh) : "l"(x));
-        asm("{\n\t.reg .u32 a;\n\tmul.lo.u32 a, %1, %3;\n\tmad.lo.u32 %0, %2, %4, a;\n\t}"
-            : "=r"(mh) : "r"(xl), "r"(xh), "r"(P2hi), "r"(P2lo));                 // off-chain
-        asm("{\n\t.reg .u64 t;\n\tmad.wide.u32 t, %2, %3, %4;\n\tmov.b64 {%0, %1}, t;\n\t}"
-            : "=r"(tlo), "=r"(thi) : "r"(xl), "r"(P2lo), "l"(w));                 // level 1
-        thi = thi + v + mh;                                                       // level 2 (IADD3)
-        rl = __funnelshift_l(thi, tlo, 31);                                       // level 3
-        rh = __funnelshift_l(tlo, thi, 31);
-        asm("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(rl), "r"(P1lo));           // level 4
-        asm("{\n\t.reg .u32 a;\n\tmul.lo.u32 a, %2, %3;\n\tmad.lo.u32 %0, %1, %4, a;\n\t}"
-            : "=r"(v) : "r"(rl), "r"(rh), "r"(P1lo), "r"(P1hi));
+    __device__ __forceinline__ void begin(uint64_t acc, uint64_t m0) {
+        const uint64_t t = acc + m0;
+        tlo = (uint32_t)t; thi = (uint32_t)(t >> 32);
     }
-    __device__ __forceinline__ uint64_t end() const { return w + ((uint64_t)v << 32); }
+    __device__ __forceinline__ void step(uint64_t m) {
+        uint32_t ml, mh, lo, hi, mhv;
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(ml), "=r"(mh) : "l"(m));
+        const uint32_t rl = __funnelshift_l(thi, tlo, 31);   // (tlo << 31) | (thi >> 1)
+        const uint32_t rh = __funnelshift_l(tlo, thi, 31);   // (thi << 31) | (tlo >> 1)
+        asm("mul.lo.u32 %0, %1, %2;" : "=r"(lo) : "r"(rl), "r"(P1lo));
+        asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(rl), "r"(P1lo));
+        asm("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %2, %3, %5;\n\tmad.lo.u32 %0, %1, %4, a;\n\t}"
+            : "=r"(mhv) : "r"(rl), "r"(rh), "r"(P1lo), "r"(P1hi), "r"(mh));
+        asm("{\n\tadd.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;\n\t}"
+            : "=r"(tlo), "=r"(thi) : "r"(lo), "r"(ml), "r"(hi), "r"(mhv));
+    }
+    __device__ __forceinline__ uint64_t end() const {
+        const uint64_t t = (uint64_t)tlo | ((uint64_t)thi << 32);
+        return rotl64(t, 31) * P1;
+    }
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -112,6 +141,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity)
         : "memory");
 }
+// Non-blocking probe of an mbarrier phase (test_wait: try_wait may SUSPEND the warp for a
+// system-dependent time when the phase is not complete, which stalled the chain it was meant to
+// overlap with).  The predicate is consumed after the stage's chain, hiding the probe's latency.
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done;
+}
+__device__ __forceinline__ uint32_t lds_volatile(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_volatile(uint32_t addr, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 // 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP.S.G).
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
@@ -122,6 +168,20 @@ __device__ __forceinline__ uint64_t lds64(uint32_t addr) {
     uint64_t v;
     asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
     return v;
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// x * P2 mod 2^64 on a 2 x 32-bit register pair (1 IMAD.WIDE + 2 IMAD)
+__device__ __forceinline__ void mulP2(uint32_t& lo, uint32_t& hi) {
+    const uint64_t m = (((uint64_t)hi << 32) | lo) * P2;
+    lo = (uint32_t)m; hi = (uint32_t)(m >> 32);
 }
 
 __device__ __forceinline__ uint64_t finish_hash(uint64_t v1, uint64_t v2, uint64_t v3, uint64_t v4, uint32_t len,
@@ -166,14 +226,24 @@ __device__ __forceinline__ uint64_t finish_hash(uint64_t v1, uint64_t v2, uint64
     return h;
 }
 
-__global__ void __launch_bounds__(kWarps * 32, 1)
+__global__ void __launch_bounds__(3 * kWarps * 32, 1)
 xxh64_blocks_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ offs,
                     const uint32_t* __restrict__ lens, uint32_t n, uint64_t* __restrict__ hashes,
                     const uint64_t* __restrict__ prior, const uint8_t* __restrict__ prior_valid,
                     uint8_t* __restrict__ changed, uint32_t* __restrict__ work_counter)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t warp_all = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    // Three warps serve each ring (ring r lives on SM sub-partition r):
+    //   warp r      TMA warp      : fetches block ids, refills drained stages with bulk copies
+    //   warp 4+r    PRE-MULTIPLY  : x -> x*P2 in place as soon as a stage has landed
+    //   warp 8+r    CHAIN warp    : the consumer; highest warp id = highest issue priority, so a
+    //                               chain never queues behind a burst of pre-multiply IMAD.WIDEs
+    // (Tried and rejected, profiles/r01_k1_variants.txt: one producer warp doing both helper jobs by
+    // polling could not keep up with a 768-cycle stage; putting the chain warps two-per-scheduler on
+    // SMSP 0,1 and all helpers on SMSP 2,3 made two chains fight over one IMAD.WIDE unit.)
+    const uint32_t role = warp_all / kWarps;                   // 0 TMA, 1 pre-multiply, 2 chains
+    const uint32_t warp = warp_all % kWarps;                   // ring this warp works on
     const uint32_t quad = lane >> 2, k = lane & 3u;
     const bool leader = (k == 0);
     const uint32_t quad_mask = 0xFu << (lane & ~3u);
@@ -182,103 +252,225 @@ xxh64_blocks_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict
     const uint32_t data_s = smem_u32(wbase);
     uint4* descs = reinterpret_cast<uint4*>(wbase + kWarpData);
     const uint32_t bars_s = smem_u32(wbase + kWarpData + kWarpDesc);
+    // Hand-offs.  TMA completion needs an mbarrier (complete_tx); the other two are plain counters in
+    // shared memory: an mbarrier arrive / test / wait costs the issuing warp ~150 cycles of blocked
+    // issue (profiles/r01_k1_timeline_mbarrier.txt: 3 such ops per 1 KiB stage cost the chains as
+    // much as 20 of their 32 rounds), a volatile LDS/STS costs it nothing.
+    const uint32_t full_s = bars_s;
+    const uint32_t ready_cnt_s = bars_s + 8 * kStages;        // stages pre-multiplied so far (pre-multiply lane 0 writes)
+    const uint32_t done_cnt_s  = ready_cnt_s + 4;              // stages drained so far       (chain lane 0 writes)
 
-    if (lane == 0) {
+    if (role == 0 && lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; s++) mbar_init(bars_s + 8 * s, kQuads);
+        for (int s = 0; s < kStages; s++) mbar_init(full_s + 8 * s, 1);   // TMA-warp lane 0 arrives with the stage's tx bytes
+        sts_volatile(ready_cnt_s, 0); sts_volatile(done_cnt_s, 0);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
+    __syncthreads();                              // the only CTA-wide barrier
+    K1_TRACE_INIT;
 
-    // ---- issue-side state (quad-uniform; every lane tracks it, the leader acts on it)
-    const uint32_t total_quads = gridDim.x * kWarps * kQuads;
-    uint32_t iss_blk = blockIdx.x + gridDim.x * (warp + kWarps * quad);  // first assignment
-    bool     iss_need_fetch = false, iss_done = false, iss_first = true;
-    uint64_t iss_off = 0;
-    uint32_t iss_rem = 0, iss_len = 0;
-    if (iss_blk < n) {
-        iss_off = offs[iss_blk]; iss_len = lens[iss_blk]; iss_rem = iss_len & ~31u;
-    } else {
-        iss_done = true;
+    if (role == 0) {
+        // =========================== TMA WARP: fetch block ids, refill ===========================
+        const uint32_t total_quads = gridDim.x * kWarps * kQuads;
+        uint32_t iss_blk = blockIdx.x + gridDim.x * (warp + kWarps * quad);  // first assignment
+        bool     iss_need_fetch = false, iss_done = false, iss_first = true;
+        uint64_t iss_off = 0;
+        uint32_t iss_rem = 0, iss_len = 0;
+        if (iss_blk < n) {
+            iss_off = offs[iss_blk]; iss_len = lens[iss_blk]; iss_rem = iss_len & ~31u;
+        } else {
+            iss_done = true;
+        }
+        // one chunk per quad into `stage` (quad-uniform state; the leader lane acts)
+        auto issue = [&](int stage) {
+            if (iss_need_fetch && !iss_done) {
+                uint32_t idx = 0;
+                if (leader) idx = total_quads + atomicAdd(work_counter, 1u);
+                idx = __shfl_sync(quad_mask, idx, lane & ~3u);
+                iss_need_fetch = false;
+                if (idx < n) {
+                    iss_blk = idx; iss_off = offs[idx]; iss_len = lens[idx]; iss_rem = iss_len & ~31u; iss_first = true;
+                } else {
+                    iss_done = true;
+                }
+            }
+            const uint32_t bar = full_s + 8 * stage;
+            uint32_t nb = 0, flags = kFlagNone;
+            if (!iss_done) {
+                nb = iss_rem < (uint32_t)kChunk ? iss_rem : (uint32_t)kChunk;
+                flags = (iss_first ? kFlagFirst : 0u) | (iss_rem == nb ? kFlagLast : 0u);
+            }
+            const bool slow = __any_sync(0xFFFFFFFFu, !iss_done && (nb != (uint32_t)kChunk || (flags & kFlagLast)));
+            const bool endd = __all_sync(0xFFFFFFFFu, iss_done);
+            const uint32_t wide = (slow ? kFlagSlow : 0u) | (endd ? kFlagEnd : 0u);
+            if (leader) descs[stage * kQuads + quad] = iss_done ? make_uint4(0, 0, kFlagNone | wide, 0) : make_uint4(nb, iss_blk, flags | wide, iss_len);
+            // one arrive for the whole stage (sum of the 8 quads' bytes), then the bulk copies
+            uint32_t tot;
+            if (!slow) {                                   // every active quad moves a full chunk
+                tot = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, leader && !iss_done)) * (uint32_t)kChunk;
+            } else {
+                tot = leader ? nb : 0u;
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
+            }
+            if (lane == 0) { if (tot) mbar_arrive_expect_tx(bar, tot); else mbar_arrive(bar); }
+            __syncwarp();
+            if (leader && nb) bulk_g2s(data_s + stage * kStageStride + quad * kQuadStride, base + iss_off, nb, bar);
+            if (!iss_done) {
+                iss_off += nb; iss_rem -= nb; iss_first = false;
+                if (flags & kFlagLast) iss_need_fetch = true;
+            }
+        };
+
+#pragma unroll
+        for (int s = 0; s < kStages; s++) issue(s);
+        for (uint32_t rf = 0;; rf++) {
+            if (__all_sync(0xFFFFFFFFu, iss_done)) break;      // an all-NONE stage is out: everyone stops there
+            const int stage = rf % kStages;
+            while (lds_volatile(done_cnt_s) <= rf) __nanosleep(20);            // the chains drained chunk rf
+            K1_TRACE(0, rf + kStages, 0);
+            issue(stage);                                                      // chunk rf + kStages
+            K1_TRACE(0, rf + kStages, 1);
+        }
+        return;
     }
 
-    auto issue = [&](int stage) {
-        if (iss_need_fetch && !iss_done) {
-            uint32_t idx = 0;
-            if (leader) idx = total_quads + atomicAdd(work_counter, 1u);
-            idx = __shfl_sync(quad_mask, idx, lane & ~3u);
-            iss_need_fetch = false;
-            if (idx < n) {
-                iss_blk = idx; iss_off = offs[idx]; iss_len = lens[idx]; iss_rem = iss_len & ~31u; iss_first = true;
-            } else {
-                iss_done = true;
-            }
-        }
-        const uint32_t bar = bars_s + 8 * stage;
-        if (iss_done) {
-            if (leader) { descs[stage * kQuads + quad] = make_uint4(0, 0, kFlagNone, 0); mbar_arrive(bar); }
-            return;
-        }
-        const uint32_t nb = iss_rem < (uint32_t)kChunk ? iss_rem : (uint32_t)kChunk;
-        const uint32_t flags = (iss_first ? kFlagFirst : 0u) | (iss_rem == nb ? kFlagLast : 0u);
-        if (leader) {
-            descs[stage * kQuads + quad] = make_uint4(nb, iss_blk, flags, iss_len);
-            if (nb) {
-                mbar_arrive_expect_tx(bar, nb);
-                bulk_g2s(data_s + stage * kStageStride + quad * kQuadStride, base + iss_off, nb, bar);
-            } else {
-                mbar_arrive(bar);
-            }
-        }
-        iss_off += nb; iss_rem -= nb; iss_first = false;
-        if (flags & kFlagLast) iss_need_fetch = true;
-    };
-
+    if (role == 1) {
+        // ================================= PRE-MULTIPLY WARP =================================
+        for (uint32_t pm = 0;; pm++) {
+            const int stage = pm % kStages;
+            mbar_wait(full_s + 8 * stage, (pm / kStages) & 1u);                // TMA bytes have landed
+            K1_TRACE(1, pm, 0);
+            // one descriptor read for the whole stage: lane l looks at quad (l & 7); ballots turn the
+            // eight byte counts into warp-uniform row masks (a quad slot = two 512-byte rows)
+            const uint4 dq = descs[stage * kQuads + (lane & 7u)];
+            const bool none = __all_sync(0xFFFFFFFFu, (dq.z & kFlagNone) != 0);
+            const uint32_t row0 = __ballot_sync(0xFFFFFFFFu, dq.x > 0u) & 0xFFu;     // quads with >= 1 row
+            const uint32_t row1 = __ballot_sync(0xFFFFFFFFu, dq.x > 512u) & 0xFFu;   // quads with 2 rows
+            K1_TRACE(1, pm, 2);
+            if (!none) {
+                // x -> x*P2 in place, 16 bytes per lane per row.  Rows are processed whole (nbytes is a
+                // multiple of 32; bytes of a last partial row beyond nbytes are never read by the
+                // chains).  Two quad slots per step: up to 4 x LDS.128 issued together, then up to
+                // 8 x (IMAD.WIDE + 2 IMAD), then the STS.128 -- every predicate is warp-uniform.
+                static_assert(kChunk == 1024 && kQuads == 8, "pre-multiply is written for 8 quads x 2 rows of 512 B");
+                uint4* const stage_rows = reinterpret_cast<uint4*>(wbase + stage * kStageStride) + lane;
+                const bool ragged = __any_sync(0xFFFFFFFFu, (dq.z & kFlagSlow) != 0);
 #pragma unroll
-    for (int s = 0; s < kStages - 1; s++) issue(s);
-
-    uint64_t acc = 0;
-    for (uint32_t it = 0;; it++) {
-        const int stage = it % kStages;
-        issue((it + kStages - 1) % kStages);   // that stage was drained in iteration it-1
-        mbar_wait(bars_s + 8 * stage, (it / kStages) & 1u);
-        const uint4 d = descs[stage * kQuads + quad];
-        if (__all_sync(0xFFFFFFFFu, (d.z & kFlagNone) != 0)) break;   // nothing left anywhere in this warp
-
-        if (!(d.z & kFlagNone)) {
-            if (d.z & kFlagFirst) {
-                // seed 0: v1 = P1+P2, v2 = P2, v3 = 0, v4 = -P1
-                acc = (k == 0) ? (P1 + P2) : (k == 1) ? P2 : (k == 2) ? 0ULL : (0ULL - P1);
-            }
-            uint32_t sp = data_s + stage * kStageStride + quad * kQuadStride + k * 8;
-            uint32_t rounds = d.x >> 5;
-            // 8 rounds per group; the next group's LDS.64 are issued before the current chain.
-            uint64_t x[8];
-            if (rounds >= 8) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) x[j] = lds64(sp + 32 * j);
-                sp += 256;
-                Chain c;
-                c.begin(acc);
-                while (rounds >= 16) {
-                    uint64_t y[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) y[j] = lds64(sp + 32 * j);
-                    sp += 256;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) c.step(x[j]);
-#pragma unroll
-                    for (int j = 0; j < 8; j++) x[j] = y[j];
-                    rounds -= 8;
+                for (int q = 0; q < kQuads; q += 2) {
+                    if (((row0 >> q) & 3u) == 0u) continue;               // both quad slots idle
+                    uint4* const r0 = stage_rows + q * (kQuadStride / 16);
+                    uint4* const r1 = r0 + kQuadStride / 16;
+                    if (!ragged) {
+                        // steady state: every busy quad has a full chunk; an idle partner slot is
+                        // multiplied too (harmless) so that the step is one branch-free block
+                        uint4 va0 = r0[0], va1 = r0[32], vb0 = r1[0], vb1 = r1[32];
+                        mulP2(va0.x, va0.y); mulP2(va0.z, va0.w); mulP2(va1.x, va1.y); mulP2(va1.z, va1.w);
+                        mulP2(vb0.x, vb0.y); mulP2(vb0.z, vb0.w); mulP2(vb1.x, vb1.y); mulP2(vb1.z, vb1.w);
+                        r0[0] = va0; r0[32] = va1; r1[0] = vb0; r1[32] = vb1;
+                    } else {
+                        const bool a0 = (row0 >> q) & 1u, a1 = (row1 >> q) & 1u, b0 = (row0 >> (q + 1)) & 1u, b1 = (row1 >> (q + 1)) & 1u;
+                        uint4 va0 = make_uint4(0, 0, 0, 0), va1 = va0, vb0 = va0, vb1 = va0;
+                        if (a0) va0 = r0[0];
+                        if (a1) va1 = r0[32];
+                        if (b0) vb0 = r1[0];
+                        if (b1) vb1 = r1[32];
+                        if (a0) { mulP2(va0.x, va0.y); mulP2(va0.z, va0.w); }
+                        if (a1) { mulP2(va1.x, va1.y); mulP2(va1.z, va1.w); }
+                        if (b0) { mulP2(vb0.x, vb0.y); mulP2(vb0.z, vb0.w); }
+                        if (b1) { mulP2(vb1.x, vb1.y); mulP2(vb1.z, vb1.w); }
+                        if (a0) r0[0] = va0;
+                        if (a1) r0[32] = va1;
+                        if (b0) r1[0] = vb0;
+                        if (b1) r1[32] = vb1;
+                    }
                 }
-#pragma unroll
-                for (int j = 0; j < 8; j++) c.step(x[j]);
-                acc = c.end();
-                rounds -= 8;
             }
-            for (; rounds; rounds--) { acc = xround(acc, lds64(sp)); sp += 32; }
+            K1_TRACE(1, pm, 3);
+            // No fence.proxy.async here: the async-proxy (TMA) refill of these bytes is issued only after
+            // the chain warp has READ what is stored here and the TMA warp has seen its hand-back, so the
+            // stores are long performed; the fence cost this warp several hundred cycles per stage.
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); sts_volatile(ready_cnt_s, pm + 1); }   // release: stage pm is consumable
+            K1_TRACE(1, pm, 1);
+            if (none) break;                                                   // the chains exit on the same stage
+        }
+        return;
+    }
 
-            if (d.z & kFlagLast) {
+    // ============================ CHAIN WARP: the four chains per block ============================
+    // Steady state (every quad of the ring is in the middle of a block, or idle): one loop iteration
+    // drains one 1 KiB chunk as a single basic block -- 32 chain steps with everything else (the next
+    // groups' LDS.64, handing the stage back, fetching the next stage's descriptor and first 8 words)
+    // scheduled into the latency shadow of the chain, whose state t (pre-rotation) is carried across
+    // chunks.  Measured before this restructuring: 21 cycles per round inside a chunk but ~500 cycles
+    // of bookkeeping between chunks (profiles/r01_k1_timeline_counters.txt).
+    // Idle quads run the same code on whatever their slot holds; the result is never looked at.
+    Chain c; c.tlo = 0; c.thi = 0;
+    while (lds_volatile(ready_cnt_s) == 0) { }
+    // seed 0: v1 = P1+P2, v2 = P2, v3 = 0, v4 = -P1
+    const uint64_t acc0 = (k == 0) ? (P1 + P2) : (k == 1) ? P2 : (k == 2) ? 0ULL : (0ULL - P1);
+    const uint32_t sp_lane = data_s + quad * kQuadStride + k * 8;
+    uint32_t it = 0, stage = 0, sp = sp_lane;
+    uint4 d = descs[quad];
+    uint64_t xa[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) xa[j] = lds64(sp + 32 * j);
+    for (;;) {
+        if (d.z & kFlagEnd) break;                                       // nothing left for this ring
+        K1_TRACE(2, it, 0);
+        const uint32_t nstage = stage + 1 == (uint32_t)kStages ? 0u : stage + 1;
+        const uint32_t nsp = sp_lane + nstage * kStageStride;
+        uint4 nd;
+        uint64_t nxa[8];
+        uint32_t next_ready;
+        if (!(d.z & kFlagSlow)) {
+            static_assert(kChunk == 1024, "the steady-state path is written for 4 groups of 8 stripes");
+            uint64_t xb[8], xc[8], xd[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) xb[j] = lds64(sp + 256 + 32 * j);
+            {
+                Chain cb; cb.begin(acc0, xa[0]);
+                c.step(xa[0]);
+                if (d.z & kFlagFirst) c = cb;
+            }
+#pragma unroll
+            for (int j = 1; j < 8; j++) c.step(xa[j]);
+#pragma unroll
+            for (int j = 0; j < 8; j++) xc[j] = lds64(sp + 512 + 32 * j);
+#pragma unroll
+            for (int j = 0; j < 8; j++) c.step(xb[j]);
+#pragma unroll
+            for (int j = 0; j < 8; j++) xd[j] = lds64(sp + 768 + 32 * j);
+            const uint32_t ready_seen = lds_volatile(ready_cnt_s);
+#pragma unroll
+            for (int j = 0; j < 8; j++) c.step(xc[j]);
+            // all of this stage's words are in registers: hand the stage back ...
+            __syncwarp();
+            if (lane == 0) sts_volatile(done_cnt_s, it + 1);
+            K1_TRACE(2, it, 1);
+            // ... and fetch the next stage's descriptor and first group speculatively (redone below
+            // in the rare case that it had not been pre-multiplied yet)
+            nd = descs[nstage * kQuads + quad];
+#pragma unroll
+            for (int j = 0; j < 8; j++) nxa[j] = lds64(nsp + 32 * j);
+#pragma unroll
+            for (int j = 0; j < 8; j++) c.step(xd[j]);
+            next_ready = ready_seen > it + 1;                            // same value in every lane
+        } else {
+            // some quad has a ragged chunk (end of a block whose length is not a multiple of the chunk,
+            // or a short block) or finishes its block here: per-quad control flow, once per block
+            const bool active = !(d.z & kFlagNone), first = (d.z & kFlagFirst) != 0;
+            uint32_t rounds = active ? (d.x >> 5) : 0u;
+            uint32_t p = sp;
+            if (rounds) {
+                if (first) c.begin(acc0, lds64(p)); else c.step(lds64(p));
+                p += 32; rounds -= 1;
+                for (; rounds; rounds--) { c.step(lds64(p)); p += 32; }
+            }
+            if (active && (d.z & kFlagLast)) {
+                // c holds t of the last stripe (or nothing for a block shorter than one stripe)
+                const uint64_t acc = (d.w >= 32) ? c.end() : 0ULL;
                 const uint32_t qb = lane & ~3u;
                 const uint64_t v1 = __shfl_sync(quad_mask, acc, qb + 0);
                 const uint64_t v2 = __shfl_sync(quad_mask, acc, qb + 1);
@@ -294,8 +486,20 @@ xxh64_blocks_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict
                     }
                 }
             }
+            __syncwarp();                                      // every lane is done reading this stage
+            if (lane == 0) sts_volatile(done_cnt_s, it + 1);   // hand it back to the TMA warp
+            next_ready = 0;
         }
-        __syncwarp();   // all lanes are done reading this stage before it is refilled
+        if (!next_ready) {                                     // (warp-uniform)
+            while (lds_volatile(ready_cnt_s) <= it + 1) { }
+            nd = descs[nstage * kQuads + quad];
+#pragma unroll
+            for (int j = 0; j < 8; j++) nxa[j] = lds64(nsp + 32 * j);
+        }
+        d = nd;
+#pragma unroll
+        for (int j = 0; j < 8; j++) xa[j] = nxa[j];
+        sp = nsp; stage = nstage; it++;
     }
 }
 
@@ -374,7 +578,7 @@ cudaError_t launch_xxh64_blocks(const HashLaunch& a, int sm_count, cudaStream_t 
     // persistent grid: one CTA per SM, never more CTAs than blocks
     uint32_t grid = (uint32_t)sm_count;
     if (a.n < grid) grid = a.n;
-    xxh64_blocks_kernel<<<grid, kWarps * 32, kSmemBytes, st>>>(a.base, a.offs, a.lens, a.n, a.hashes, a.prior,
+    xxh64_blocks_kernel<<<grid, 3 * kWarps * 32, kSmemBytes, st>>>(a.base, a.offs, a.lens, a.n, a.hashes, a.prior,
                                                               a.prior_valid, a.changed, a.work_counter);
     return cudaGetLastError();
 }
