@@ -203,7 +203,6 @@ def main() -> None:
     launches += 2 * args.steps
     k1_ms = [res.run(1)[0] for _ in range(max(3, args.steps))]       # the dominant kernel alone
     launches += 2 * len(k1_ms)
-    clk = clocks.stop()
     hashes_dev, surv = res.results()
     assert len(surv) == n_blocks
     res.close()
@@ -230,6 +229,7 @@ def main() -> None:
                 assert filecmp.cmp(src / "f00003.bin", dst / "f00003.bin", shallow=False), "copied bytes differ"
                 assert stats["bytes_total"] == nbytes and stats["blocks_total"] == n_blocks
         e2e_v = world * nbytes * len(e2e_times) / sum(e2e_times) / GiB
+        clk = clocks.stop()          # sampled over both timed regions (HBM-resident passes and end-to-end steps)
 
         line = None
         if rank == 0:

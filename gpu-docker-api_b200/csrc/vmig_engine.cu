@@ -86,6 +86,7 @@ public:
 };
 
 static void bind_thread(const DeviceInfo& d);
+static void bind_thread_complement(const DeviceInfo& d);
 
 // The pinned rings are allocated and first-touched by a thread bound to the GPU's NUMA-local
 // CPUs, so that staging copies and both DMA directions stay on the GPU's socket (on the 2-socket
@@ -295,6 +296,15 @@ int io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested,
     return VMIG_OK;
 }
 
+static void bind_thread_complement(const DeviceInfo& d) {
+    if (d.cpus.empty()) return;
+    cpu_set_t cur, set; CPU_ZERO(&cur); CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof cur, &cur) != 0) return;
+    for (int c = 0; c < CPU_SETSIZE; c++) if (CPU_ISSET(c, &cur)) CPU_SET(c, &set);
+    for (int c : d.cpus) if (c < CPU_SETSIZE) CPU_CLR(c, &set);
+    if (CPU_COUNT(&set) > 0) sched_setaffinity(0, sizeof set, &set);
+}
+
 // ---------------------------------------------------------------------------------------------
 // blocking queue
 template <class T>
@@ -337,6 +347,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
     const uint32_t slot_bytes = pipe->slot_bytes;
     const long fail_block = env_long("VMIG_FAIL_BLOCK", -1);
     const bool bind_io = env_long("VMIG_BIND_IO", 1) != 0;      // reader/writer threads on the GPU's socket
+    const long bind_wr = env_long("VMIG_BIND_WRITERS", 1);      // 1 GPU-local CPUs, 0 unbound, 2 the other CPUs
 
     auto set_err = [&](int code) {
         int expect = 0;
@@ -585,7 +596,8 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
     std::vector<std::thread> writers;
     for (uint32_t t = 0; t < n_writers; t++)
         writers.emplace_back([&, t] {
-            if (bind_io) bind_thread(pipe->dev);
+            if (bind_io && bind_wr == 1) bind_thread(pipe->dev);
+            else if (bind_io && bind_wr == 2) bind_thread_complement(pipe->dev);
             IoTask k;
             while (write_qs[t]->pop(&k)) {
                 Slot& sl = pipe->slots[k.batch->slot];
