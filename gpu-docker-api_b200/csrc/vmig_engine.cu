@@ -288,9 +288,11 @@ int io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested,
         long ncpu = sched_getaffinity(0, sizeof cur, &cur) == 0 ? CPU_COUNT(&cur) : sysconf(_SC_NPROCESSORS_ONLN);
         int ngpu = 1; if (cudaGetDeviceCount(&ngpu) != cudaSuccess) { cudaGetLastError(); ngpu = 1; }
         long share = std::max<long>(lanes, (size_t)ngpu);         // other GPUs may be busy migrating too
-        long budget = std::min<long>(32, std::max<long>(4, ncpu / share));
-        if (r <= 0) r = std::max<long>(2, budget * 3 / 8);
-        if (w <= 0) w = std::max<long>(2, budget - r);
+        // measured on the 2-socket bench box (profiles/r01_e2e_threads.txt): the copy threads are
+        // memory-bound, more of them than ~8 readers + ~12 writers per GPU only adds contention
+        long budget = std::min<long>(24, std::max<long>(4, ncpu / share));
+        if (r <= 0) r = std::max<long>(2, budget / 3);
+        if (w <= 0) w = std::max<long>(2, budget / 2);
     }
     *readers = (uint32_t)std::min<long>(r, 64); *writers = (uint32_t)std::min<long>(w, 64);
     return VMIG_OK;
@@ -347,7 +349,10 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
     const uint32_t slot_bytes = pipe->slot_bytes;
     const long fail_block = env_long("VMIG_FAIL_BLOCK", -1);
     const bool bind_io = env_long("VMIG_BIND_IO", 1) != 0;      // reader/writer threads on the GPU's socket
-    const long bind_wr = env_long("VMIG_BIND_WRITERS", 1);      // 1 GPU-local CPUs, 0 unbound, 2 the other CPUs
+    // writers default to the CPUs of the OTHER socket(s): destination pages then land in that socket's
+    // DRAM and the GPU-local socket (pinned rings, both DMA directions, the readers) is relieved of a
+    // third of the traffic (+15% end to end on the bench box); 1 = GPU-local CPUs, 0 = unbound
+    const long bind_wr = env_long("VMIG_BIND_WRITERS", 2);
 
     auto set_err = [&](int code) {
         int expect = 0;

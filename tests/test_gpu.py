@@ -394,6 +394,68 @@ def test_multi_gpu_sharding_same_result(vm, orc, shm_tmp):
     assert orc.compare_trees(d1, d2, mtime_ns=True) == []
 
 
+def test_full_size_resident_pass_properties(vm, orc):
+    """BASELINE config 2 size (10 GiB = 2 560 blocks resident in HBM): sampled blocks == oracle, the
+    30 % mutation of config 4 is found exactly, and hashing is deterministic across passes."""
+    n, bb = 2560, 4 * MiB
+    r = vm.Resident(n, bb)
+    try:
+        r.fill(0xB200)
+        r.set_prior(None)
+        r.run(1)
+        h1, surv = r.results()
+        assert len(surv) == n
+        words = bb // 8
+        for b in [0, 1, 147, 148, 1279, 2047, 2559]:
+            assert int(h1[b]) == orc.xxh64(orc.splitmix_bytes(0xB200, bb, first_word=b * words)), b
+        r.run(2)
+        h1b, _ = r.results()
+        assert (h1 == h1b).all()
+        flip = np.sort(np.random.default_rng(44).permutation(n)[: n * 3 // 10]).astype(np.uint64)
+        r.set_prior(h1, np.ones(n, np.uint8))
+        r.flip(flip)
+        r.run(1)
+        h2, surv = r.results()
+        assert surv.tolist() == flip.tolist() and len(surv) == 768
+        r.flip(flip)                       # flipping back restores every hash (involution)
+        r.run(1)
+        h3, surv = r.results()
+        assert (h3 == h1).all() and len(surv) == 0
+    finally:
+        r.close()
+
+
+def test_full_size_rollback_diff_properties(vm, orc, shm_tmp):
+    """BASELINE config 4 at 10 GiB: 30 % of the blocks differ from the prior version; exactly those
+    travel back over PCIe and are written, and the destination ends up identical to the source
+    (block table of dst == block table of src; two whole files re-hashed by the oracle)."""
+    src, dst = shm_tmp / "src", shm_tmp / "dst"
+    dst.mkdir()
+    nf, fb, bb = 10, 1 << 30, 4 * MiB
+    vm.datagen_files(src, 4, nf, fb, threads=32)
+    st0 = vm.migrate_tree(src, dst, None, shm_tmp / "v1.vmig")              # dst := v1, with its table
+    assert st0["blocks_total"] == 2560 and st0["blocks_skipped"] == 0
+    nblk = nf * fb // bb
+    changed = np.sort(np.random.default_rng(44).permutation(nblk)[: nblk * 3 // 10])
+    for g in changed:                                                         # block g of the table = file g//256, block g%256
+        with open(src / f"f{g // 256:05d}.bin", "r+b") as f:
+            f.seek((g % 256) * bb)
+            w = bytes(x ^ 0xFF for x in f.read(8))
+            f.seek((g % 256) * bb)
+            f.write(w)
+    st = vm.migrate_tree(src, dst, shm_tmp / "v1.vmig", shm_tmp / "v2.vmig")
+    assert st["blocks_total"] - st["blocks_skipped"] == len(changed) == 768
+    assert st["bytes_d2h"] == st["bytes_written"] == 768 * bb and st["bytes_h2d"] == nf * fb
+    t1, t2 = vm.table_hashes(shm_tmp / "v1.vmig"), vm.table_hashes(shm_tmp / "v2.vmig")
+    assert np.nonzero(t1 != t2)[0].tolist() == changed.tolist()
+    vm.hash_tree(dst, shm_tmp / "dst.vmig")
+    assert (vm.table_hashes(shm_tmp / "dst.vmig") == t2).all()              # dst == src, block for block
+    for name in ("f00000.bin", "f00007.bin"):
+        want = orc.hash_file(src / name)
+        k = int(name[1:6]) * 256
+        assert (t2[k:k + 256] == want).all() and (orc.hash_file(dst / name) == want).all()
+
+
 def test_smoke_entry_point():
     import __graft_entry__ as g
     g.smoke()
