@@ -134,6 +134,7 @@ public:
     bool src_pinned = false, dst_pinned = false;
     int read_block(const BlockRef& b, uint8_t* d) override { if (b.len) memcpy(d, src + b.file_off, b.len); return VMIG_OK; }
     int write_block(const BlockRef& b, const uint8_t* s) override { if (b.len) memcpy(dst + b.file_off, s, b.len); return VMIG_OK; }
+    uint32_t write_key(const BlockRef& b) override { return (uint32_t)b.table_idx; }
     const uint8_t* pinned_src(const BlockRef& b) override { return src_pinned ? src + b.file_off : nullptr; }
     uint8_t* pinned_dst(const BlockRef& b) override { return dst_pinned ? dst + b.file_off : nullptr; }
 };
@@ -167,7 +168,11 @@ int run_blocks(const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior,
         }
     }
     uint32_t readers, writers;
-    io_threads_default(&readers, &writers, o.io_threads, lanes);
+    {
+        uint32_t distinct = 0, last = 0xFFFFFFFFu;               // blocks are interleaved across <= 64 files
+        for (size_t i = 0; i < blocks.size() && i < 256 && distinct < 32; i++) if (blocks[i].file != last) { distinct++; last = blocks[i].file; }
+        io_threads_default(&readers, &writers, o.io_threads, lanes, distinct >= 32);
+    }
     std::vector<Pipe*> pipes(lanes, nullptr);
     for (size_t i = 0; i < lanes; i++) {
         rc = ctx_acquire_pipe(devs[i], &pipes[i]);

@@ -279,7 +279,7 @@ void ctx_release_pipe(Pipe* p)
     p->destroy(); delete p;    // context was shut down underneath us
 }
 
-int io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested, size_t lanes)
+int io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested, size_t lanes, bool many_files)
 {
     long r = env_long("VMIG_READERS", 0), w = env_long("VMIG_WRITERS", 0);
     if (requested) { r = (requested + 1) * 2 / 5; w = requested - r; }
@@ -291,7 +291,9 @@ int io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested,
         // measured on the 2-socket bench box (profiles/r01_e2e_threads.txt): the copy threads are
         // memory-bound, more of them than ~8 readers + ~12 writers per GPU only adds contention
         long budget = std::min<long>(24, std::max<long>(4, ncpu / share));
-        if (r <= 0) r = std::max<long>(2, budget / 3);
+        // few large files: the destination serialises per file, extra readers only steal memory
+        // bandwidth from the writers; many files: reads are the longer pole
+        if (r <= 0) r = std::max<long>(2, many_files ? budget / 2 : budget / 3);
         if (w <= 0) w = std::max<long>(2, budget / 2);
     }
     *readers = (uint32_t)std::min<long>(r, 64); *writers = (uint32_t)std::min<long>(w, 64);
@@ -593,7 +595,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
             }
             if (tasks.empty()) { finish_batch(b); continue; }
             b->writes_left.store((int)tasks.size());
-            for (auto& t : tasks) write_qs[blocks[t.i0].file % n_writers]->push(t);
+            for (auto& t : tasks) write_qs[io->write_key(blocks[t.i0]) % n_writers]->push(t);
         }
     });
 

@@ -37,6 +37,9 @@ public:
     virtual int  write_block(const BlockRef& b, const uint8_t* src) = 0;
     // called exactly once per block when it needs nothing more (written == false: skipped)
     virtual int  block_done(const BlockRef&, bool /*written*/) { return VMIG_OK; }
+    // writes with the same key are issued by one writer thread, in order (a file takes writes from one
+    // thread at a time anyway); backends without such a constraint spread the keys
+    virtual uint32_t write_key(const BlockRef& b) { return b.file; }
     // non-null: page-locked memory the DMA engines can use directly (no staging copy)
     virtual const uint8_t* pinned_src(const BlockRef&) { return nullptr; }
     virtual uint8_t*       pinned_dst(const BlockRef&) { return nullptr; }
@@ -64,7 +67,7 @@ int  ctx_select(uint32_t mask, std::vector<DeviceInfo>* out);
 int  ctx_acquire_pipe(const DeviceInfo& d, Pipe** out);
 void ctx_release_pipe(Pipe* p);
 uint32_t pipe_slot_bytes();
-int  io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested, size_t lanes);
+int  io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested, size_t lanes, bool many_files);
 
 // Run blocks[] through one GPU.  hashes_out[b.table_idx] receives every block's hash.
 //   hash_only : no D2H of data, no writes (block_done(b,false) is still called).
