@@ -35,6 +35,7 @@
 //    batch spreads over all SMs first, then over the 4 sub-partitions; afterwards quads pull
 //    indices from the atomic counter (ragged block lengths balance).
 #include "vmig_kernels.cuh"
+#include <atomic>
 
 namespace vmig {
 
@@ -141,15 +142,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity)
         : "memory");
 }
-// Non-blocking probe of an mbarrier phase (test_wait: try_wait may SUSPEND the warp for a
-// system-dependent time when the phase is not complete, which stalled the chain it was meant to
-// overlap with).  The predicate is consumed after the stage's chain, hiding the probe's latency.
-__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    return done;
-}
 __device__ __forceinline__ uint32_t lds_volatile(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
@@ -170,14 +162,6 @@ __device__ __forceinline__ uint64_t lds64(uint32_t addr) {
     return v;
 }
 
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 // x * P2 mod 2^64 on a 2 x 32-bit register pair (1 IMAD.WIDE + 2 IMAD)
 __device__ __forceinline__ void mulP2(uint32_t& lo, uint32_t& hi) {
     const uint64_t m = (((uint64_t)hi << 32) | lo) * P2;
@@ -564,14 +548,14 @@ size_t xxh64_blocks_smem_bytes() { return kSmemBytes; }
 cudaError_t launch_xxh64_blocks(const HashLaunch& a, int sm_count, cudaStream_t st)
 {
     if (a.n == 0) return cudaSuccess;
-    static thread_local bool attr_set[64] = {};
+    static std::atomic<uint64_t> attr_set{0};     // bit d: dynamic shared memory opt-in done on device d
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 64 && !attr_set[dev]) {
+    if (dev >= 64 || !(attr_set.load(std::memory_order_acquire) & (1ull << dev))) {
         e = cudaFuncSetAttribute(xxh64_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return e;
-        attr_set[dev] = true;
+        if (dev < 64) attr_set.fetch_or(1ull << dev, std::memory_order_release);
     }
     e = cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;

@@ -158,6 +158,50 @@ def test_copydir_matches_reference_tar_pipeline(vm, orc, shm_tmp):
     assert (src / "big.bin").exists()
 
 
+def test_copydir_awkward_names_and_shapes(vm, orc, shm_tmp):
+    """Names tar has to escape or extend (spaces, newline, non-UTF-8 bytes, >100 and >255 byte paths),
+    read-only and setgid directories, a sparse file (tar densifies it), hard-linked empty files,
+    a symlink to a directory, an empty source subtree."""
+    src, dst, ref = shm_tmp / "src", shm_tmp / "dst", shm_tmp / "ref"
+    for d in (src, dst, ref):
+        d.mkdir()
+    bsrc = os.fsencode(src)
+    names = [b"sp ace", b"new\nline", b"tab\there", b"quote'\"", b"\xff\xfe-not-utf8", "uni-\u00e7o\u2202\u00e9".encode(), b"-dash", b"x" * 200]
+    for i, n in enumerate(names):
+        with open(os.path.join(bsrc, n), "wb") as f:
+            f.write(orc.splitmix_bytes(90 + i, 1000 * i + 1).tobytes())
+    deep = src
+    for i in range(12):                                   # 12 x 30 = 360-byte relative path
+        deep = deep / ("d%02d_" % i + "y" * 25)
+    deep.mkdir(parents=True)
+    (deep / "leaf.bin").write_bytes(orc.splitmix_bytes(70, 4 * MiB + 17).tobytes())
+    (src / "ro_dir").mkdir(); (src / "ro_dir" / "inside").write_bytes(b"in a read-only dir")
+    os.chmod(src / "ro_dir", 0o555)
+    (src / "sgid").mkdir(); os.chmod(src / "sgid", 0o2775)
+    with open(src / "sparse.bin", "wb") as f:             # 6 MiB hole, then data
+        f.seek(6 * MiB); f.write(b"tail-after-hole")
+    (src / "e1").write_bytes(b""); os.link(src / "e1", src / "e2")
+    os.symlink("ro_dir", src / "dirlink")
+    (src / "empty_tree" / "a" / "b").mkdir(parents=True)
+    vm.CopyDir(str(src), str(dst))
+    assert orc.ref_copy(src, ref).returncode == 0
+    assert orc.compare_trees(ref, dst, mtime_ns=True) == []
+    assert os.lstat(dst / "e1").st_ino == os.lstat(dst / "e2").st_ino
+    assert (dst / "sparse.bin").stat().st_size == 6 * MiB + 15
+    os.chmod(src / "ro_dir", 0o755)                       # let the fixture clean up
+    os.chmod(dst / "ro_dir", 0o755), os.chmod(ref / "ro_dir", 0o755)
+
+
+def test_copydir_of_empty_directory(vm, orc, shm_tmp):
+    src, dst = shm_tmp / "src", shm_tmp / "dst"
+    src.mkdir(), dst.mkdir()
+    os.chmod(src, 0o750)
+    st = vm.migrate_tree(src, dst, None, shm_tmp / "t.vmig")
+    assert st["blocks_total"] == 0 and st["kernel_launches"] == 0 and os.listdir(dst) == []
+    assert os.stat(dst).st_mode & 0o7777 == 0o750
+    assert orc.read_table(shm_tmp / "t.vmig")["entries"] == []
+
+
 def test_block_table_matches_oracle(vm, orc, shm_tmp):
     src, dst = shm_tmp / "src", shm_tmp / "dst"
     src.mkdir(), dst.mkdir()
