@@ -32,8 +32,8 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libvmig.so"
 
 VMIG_OK, VMIG_EINVAL, VMIG_ENOGPU, VMIG_ECUDA, VMIG_EIO = 0, -1, -2, -3, -4
-VMIG_ENOMEM, VMIG_ETABLE, VMIG_EFAULT, VMIG_ENOTDIR, VMIG_ESRCCHANGED = -5, -6, -7, -8, -9
-F_MOVE_SRC, F_SKIP_HIDDEN_TOPDIRS, F_MTIME_NS, F_NO_METADATA, F_HASH_ONLY = 0x01, 0x02, 0x04, 0x08, 0x10
+VMIG_ENOMEM, VMIG_ETABLE, VMIG_EFAULT, VMIG_ENOTDIR, VMIG_ESRCCHANGED, VMIG_EVERIFY = -5, -6, -7, -8, -9, -10
+F_MOVE_SRC, F_SKIP_HIDDEN_TOPDIRS, F_MTIME_NS, F_NO_METADATA, F_HASH_ONLY, F_VERIFY = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
 BLOCK_BYTES = 4 << 20
 
 EXPORTS = [
@@ -213,8 +213,9 @@ def ToBytes(origin: str) -> int:
 # ------------------------------------------------------------------------------------------------
 # engine entry points
 def migrate_tree(src, dst, prior_table=None, out_table=None, *, gpu_mask: int = 0, flags: int = 0,
-                 block_bytes: int = 0, io_threads: int = 0) -> dict:
-    o = Opts(gpu_mask=gpu_mask, block_bytes=block_bytes, flags=flags, io_threads=io_threads)
+                 block_bytes: int = 0, io_threads: int = 0, streams_per_gpu: int = 0) -> dict:
+    o = Opts(gpu_mask=gpu_mask, block_bytes=block_bytes, flags=flags, io_threads=io_threads,
+             streams_per_gpu=streams_per_gpu)
     st = Stats()
     _check(_lib.vmig_migrate_tree(_b(src), _b(dst), _b(prior_table), _b(out_table), C.byref(o), C.byref(st)),
            f"vmig_migrate_tree({src} -> {dst})")

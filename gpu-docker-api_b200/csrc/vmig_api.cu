@@ -35,6 +35,7 @@ public:
     const Manifest* m = nullptr;
     MetaPolicy pol;
     bool hash_only = false;
+    long corrupt_block = -1;             // VMIG_CORRUPT_BLOCK test hook: flip one bit of this block on its way to disk
     std::unique_ptr<FS[]> fs;
     std::mutex stripes[64];
 
@@ -93,6 +94,14 @@ public:
     int write_block(const BlockRef& b, const uint8_t* src) override {
         int fd; int rc = open_dst(b.file, &fd);
         if (rc) return rc;
+        if (corrupt_block >= 0 && (uint64_t)corrupt_block == b.table_idx && b.len) {
+            const uint8_t bad = src[0] ^ 1u;           // what VMIG_F_VERIFY exists to catch
+            if (pwrite(fd, &bad, 1, (off_t)b.file_off) != 1) return fail(VMIG_EIO, "pwrite (fault hook)");
+            if (b.len == 1) return VMIG_OK;
+            size_t put1 = 1;
+            while (put1 < b.len) { ssize_t w = pwrite(fd, src + put1, b.len - put1, (off_t)(b.file_off + put1)); if (w <= 0) return fail(VMIG_EIO, "pwrite (fault hook)"); put1 += (size_t)w; }
+            return VMIG_OK;
+        }
         size_t put = 0;
         while (put < b.len) {
             ssize_t w = pwrite(fd, src + put, b.len - put, (off_t)(b.file_off + put));
@@ -183,7 +192,7 @@ int run_blocks(const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior,
     std::vector<std::thread> th;
     for (size_t i = 0; i < lanes; i++)
         th.emplace_back([&, i] {
-            run_lane(pipes[i], share[i], io, has_prior, hash_only, readers, writers, hashes, &ls[i], &err, &err_msg, &err_mu);
+            run_lane(pipes[i], share[i], io, has_prior, hash_only, readers, writers, o.streams_per_gpu, hashes, &ls[i], &err, &err_msg, &err_mu);
         });
     for (auto& t : th) t.join();
     for (size_t i = 0; i < lanes; i++) ctx_release_pipe(pipes[i]);
@@ -243,6 +252,7 @@ int migrate_tree_impl(const char* src_dir, const char* dst_dir, const char* prio
     }
     FileIO io;
     io.src_root = src; io.dst_root = dst; io.m = &man; io.pol = default_meta_policy(o.flags); io.hash_only = hash_only;
+    io.corrupt_block = env_long("VMIG_CORRUPT_BLOCK", -1);
     io.fs.reset(new FileIO::FS[man.files.size() ? man.files.size() : 1]);
     std::vector<uint64_t> hashes(man.n_blocks, 0);
 
@@ -319,6 +329,30 @@ int migrate_tree_impl(const char* src_dir, const char* dst_dir, const char* prio
     }
     st.ns_meta = now_ns() - t0;
 
+    if ((o.flags & VMIG_F_VERIFY) && !hash_only) {
+        // read the destination back through the same GPU path (hash only) and compare block tables
+        FileIO vio;
+        vio.src_root = dst; vio.dst_root = dst; vio.m = &man; vio.pol = io.pol; vio.hash_only = true;
+        vio.fs.reset(new FileIO::FS[man.files.size() ? man.files.size() : 1]);
+        for (uint32_t f = 0; f < man.files.size(); f++) {
+            const Entry& e = man.files[f];
+            if (e.hardlink_of >= 0 || e.n_blocks == 0) continue;
+            vio.fs[f].reads_left.store((uint32_t)e.n_blocks); vio.fs[f].blocks_left.store((uint32_t)e.n_blocks);
+        }
+        std::vector<BlockRef> vblocks = blocks;
+        for (auto& b : vblocks) { b.prior_hash = 0; b.prior_valid = 0; }
+        std::vector<uint64_t> vh(man.n_blocks, 0);
+        vmig_stats vst; memset(&vst, 0, sizeof vst);
+        rc = run_blocks(vblocks, &vio, false, true, o, vh.data(), &vst);
+        if (rc) { std::string keep = last_error_cstr(); vio.close_all(man.files.size()); set_last_error_str(keep); return rc; }
+        st.kernel_launches += vst.kernel_launches; st.ms_kernel += vst.ms_kernel; st.bytes_h2d += vst.bytes_h2d;
+        for (auto& b : vblocks)
+            if (vh[b.table_idx] != hashes[b.table_idx])
+                return fail(VMIG_EVERIFY, "verify: %s block %llu hashes %016llx in the destination, %016llx in the source",
+                            man.files[b.file].rel.c_str(), (unsigned long long)(b.file_off / o.block_bytes),
+                            (unsigned long long)vh[b.table_idx], (unsigned long long)hashes[b.table_idx]);
+    }
+
     t0 = now_ns();
     if (out_path && *out_path) {
         BlockTable t; t.block_bytes = o.block_bytes; t.algo = 1;
@@ -362,6 +396,7 @@ const char* vmig_strerror(int code)
     case VMIG_EFAULT: return "injected fault";
     case VMIG_ENOTDIR: return "not a directory";
     case VMIG_ESRCCHANGED: return "source changed during migration";
+    case VMIG_EVERIFY: return "destination does not verify against the source";
     default: return "unknown vmig error";
     }
 }

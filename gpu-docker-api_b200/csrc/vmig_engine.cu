@@ -344,7 +344,7 @@ static void bind_thread(const DeviceInfo& d) {
 }
 
 int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior, bool hash_only,
-             uint32_t n_readers, uint32_t n_writers, uint64_t* hashes_out, LaneStats* stats,
+             uint32_t n_readers, uint32_t n_writers, uint32_t max_slots, uint64_t* hashes_out, LaneStats* stats,
              std::atomic<int>* err, std::string* err_msg, std::mutex* err_mu)
 {
     if (blocks.empty()) return VMIG_OK;
@@ -382,7 +382,8 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
     const size_t n_batches = batches.size();
 
     BQ<int> free_slots;
-    for (int s = 0; s < (int)pipe->slots.size(); s++) free_slots.push(s);
+    const int use_slots = max_slots ? (int)std::min<size_t>(max_slots, pipe->slots.size()) : (int)pipe->slots.size();
+    for (int s = 0; s < use_slots; s++) free_slots.push(s);     // one side stream per slot in use
     BQ<IoTask> read_q;
     // one queue per writer, keyed by destination file: a file accepts writes from one thread at
     // a time anyway (inode lock), so two writers on one file only queue up behind each other

@@ -73,7 +73,7 @@ int  io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested
 //   hash_only : no D2H of data, no writes (block_done(b,false) is still called).
 //   err       : call-wide first-error latch shared by all lanes (0 = fine).
 int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior, bool hash_only,
-             uint32_t readers, uint32_t writers, uint64_t* hashes_out, LaneStats* stats,
+             uint32_t readers, uint32_t writers, uint32_t max_slots, uint64_t* hashes_out, LaneStats* stats,
              std::atomic<int>* err, std::string* err_msg, std::mutex* err_mu);
 
 }  // namespace vmig

@@ -52,6 +52,7 @@ extern "C" {
 #define VMIG_EFAULT     (-7)   /* injected fault (VMIG_FAIL_BLOCK test hook)                    */
 #define VMIG_ENOTDIR    (-8)   /* src or dst is not a directory (reference utils/file.go:50-59)  */
 #define VMIG_ESRCCHANGED (-9)  /* a source file shrank while it was being read                  */
+#define VMIG_EVERIFY    (-10)  /* VMIG_F_VERIFY: a destination block does not hash like its source */
 
 /* ---- lifecycle --------------------------------------------------------------------------- */
 /* Idempotent, thread-safe.  gpu_mask bit i selects CUDA device i; 0 = all visible devices.
@@ -74,12 +75,14 @@ const char* vmig_version(void);
                                            format keeps whole seconds only -> default off)         */
 #define VMIG_F_NO_METADATA       0x08u  /* data only: no chown/chmod/utimens                       */
 #define VMIG_F_HASH_ONLY         0x10u  /* build the block table of src; dst is not touched        */
-#define VMIG_F_NO_ZEROCOPY       0x20u  /* force the staged (pread/memcpy) host path               */
+#define VMIG_F_VERIFY            0x20u  /* after the copy, re-read the DESTINATION through the GPU and
+                                           require its block hashes to equal the source's; with
+                                           VMIG_F_MOVE_SRC the source is only unlinked if they do    */
 
 typedef struct vmig_opts {
     uint32_t gpu_mask;         /* 0 = every initialised GPU; blocks are sharded across the set   */
     uint32_t block_bytes;      /* 0 -> 4 MiB (4194304); must be a multiple of 4096               */
-    uint32_t streams_per_gpu;  /* 0 -> default (4)                                               */
+    uint32_t streams_per_gpu;  /* side streams = staging slots in flight per GPU; 0 -> all (16)   */
     uint32_t flags;            /* VMIG_F_*                                                       */
     uint32_t io_threads;       /* 0 -> default: host reader+writer threads per GPU               */
     uint32_t reserved[3];

@@ -1,0 +1,81 @@
+//go:build vmig
+
+package utils
+
+/*
+#cgo LDFLAGS: -lvmig -lstdc++ -lpthread -ldl -lrt
+#include <stdlib.h>
+#include <vmig.h>
+*/
+import "C"
+
+import (
+	"unsafe"
+
+	"github.com/ngaut/log"
+	"github.com/pkg/errors"
+)
+
+func vmigErr(rc C.int, what string) error {
+	if rc == 0 {
+		return nil
+	}
+	return errors.Errorf("%s: %s (%d): %s", what, C.GoString(C.vmig_strerror(rc)), int(rc),
+		C.GoString(C.vmig_last_error())) // thread-local: cgo keeps the goroutine on its OS thread for the call
+}
+
+// CopyDir replaces `sh -c "(cd src; tar c .) | (cd dest; tar x)"` (utils/copy.go:17-27).
+func CopyDir(src, dest string) error {
+	cs, cd := C.CString(src), C.CString(dest)
+	defer C.free(unsafe.Pointer(cs))
+	defer C.free(unsafe.Pointer(cd))
+	return errors.Wrapf(vmigErr(C.vmig_copy_dir(cs, cd), "vmig_copy_dir"),
+		"vmig copy failed, src:%s, dest: %s", src, dest)
+}
+
+// CopyDirDiff is CopyDir with the block tables the diff-skip path needs. prior/out are paths
+// under the per-version directory setToMergeMap already creates
+// (internal/services/replicaset.go:681-704): merges/<rs>/<rs>-<v>/blocks.vmig.
+func CopyDirDiff(src, dest, priorTable, outTable string) error {
+	cs, cd := C.CString(src), C.CString(dest)
+	defer C.free(unsafe.Pointer(cs))
+	defer C.free(unsafe.Pointer(cd))
+	var cp, co *C.char
+	if priorTable != "" {
+		cp = C.CString(priorTable)
+		defer C.free(unsafe.Pointer(cp))
+	}
+	if outTable != "" {
+		co = C.CString(outTable)
+		defer C.free(unsafe.Pointer(co))
+	}
+	var st C.vmig_stats
+	rc := C.vmig_migrate_tree(cs, cd, cp, co, nil, &st)
+	if rc == 0 {
+		log.Infof("vmig: %d bytes, %d/%d blocks skipped, %.2f GiB/s", uint64(st.bytes_total),
+			uint64(st.blocks_skipped), uint64(st.blocks_total),
+			float64(st.bytes_total)/float64(st.ns_total)*1e9/(1<<30))
+	}
+	return vmigErr(rc, "vmig_migrate_tree")
+}
+
+// CopyOldMergedToNewContainerMerged (utils/copy.go:31-46): unchanged except for the callee.
+// GetContainerMergedLayer (Docker ContainerInspect -> UpperDir, utils/copy.go:48-54) stays in Go.
+
+// CopyOldMountPointToContainerMountPoint replaces moveVolumeData's helper container + `mv`
+// (utils/copy.go:74-128): resolve both volume names with GetVolumeMountPoint (utils/copy.go:65-72,
+// kept) and move on the host paths, synchronously, with the status checked.
+func CopyOldMountPointToContainerMountPoint(oldVolume, newVolume string) error {
+	src, err := GetVolumeMountPoint(oldVolume)
+	if err != nil {
+		return errors.WithMessage(err, "GetVolumeMountPoint failed")
+	}
+	dst, err := GetVolumeMountPoint(newVolume)
+	if err != nil {
+		return errors.WithMessage(err, "GetVolumeMountPoint failed")
+	}
+	cs, cd := C.CString(src), C.CString(dst)
+	defer C.free(unsafe.Pointer(cs))
+	defer C.free(unsafe.Pointer(cd))
+	return errors.WithMessage(vmigErr(C.vmig_move_dir(cs, cd), "vmig_move_dir"), "moveData failed")
+}

@@ -384,6 +384,40 @@ def test_injected_fault_is_reported_not_swallowed(vm, orc, shm_tmp, monkeypatch)
     assert (dst / "x.bin").read_bytes() == (src / "x.bin").read_bytes()
 
 
+def test_verify_flag_catches_a_corrupted_destination(vm, orc, shm_tmp, monkeypatch):
+    """VMIG_F_VERIFY re-reads the destination through the GPU; a block that reached the disk wrong
+    (test hook flips one bit while writing) fails the call, and a move then keeps its source."""
+    src, dst = shm_tmp / "src", shm_tmp / "dst"
+    src.mkdir(), dst.mkdir()
+    (src / "a.bin").write_bytes(orc.splitmix_bytes(3, 13 * MiB + 5).tobytes())
+    (src / "b.bin").write_bytes(orc.splitmix_bytes(4, 6 * MiB).tobytes())
+    st = vm.migrate_tree(src, dst, None, shm_tmp / "t.vmig", flags=vm.F_VERIFY)          # clean run verifies
+    assert st["bytes_h2d"] == 2 * st["bytes_total"] and st["bytes_d2h"] == st["bytes_total"]
+    monkeypatch.setenv("VMIG_CORRUPT_BLOCK", "2")
+    shutil.rmtree(dst); dst.mkdir()
+    with pytest.raises(vm.VmigError) as ei:
+        vm.migrate_tree(src, dst, None, None, flags=vm.F_VERIFY | vm.F_MOVE_SRC)
+    assert ei.value.code == vm.VMIG_EVERIFY and "a.bin block 2" in str(ei.value)
+    assert (src / "a.bin").exists() and (src / "b.bin").exists()          # nothing was unlinked
+    vm.migrate_tree(src, dst, None, None)                                 # without VERIFY the bad bit goes unnoticed ...
+    assert (dst / "a.bin").read_bytes() != (src / "a.bin").read_bytes()   # ... which is what the flag is for
+    monkeypatch.delenv("VMIG_CORRUPT_BLOCK")
+    vm.migrate_tree(src, dst, None, None, flags=vm.F_VERIFY | vm.F_MOVE_SRC)
+    assert os.listdir(src) == [] and sorted(os.listdir(dst)) == ["a.bin", "b.bin"]
+
+
+def test_side_stream_limit_option(vm, orc, shm_tmp):
+    """vmig_opts.streams_per_gpu bounds the staging slots (= side streams) in flight; results are identical."""
+    src, d1, d2 = shm_tmp / "src", shm_tmp / "d1", shm_tmp / "d2"
+    src.mkdir(), d1.mkdir(), d2.mkdir()
+    for i in range(3):
+        (src / f"f{i}").write_bytes(orc.splitmix_bytes(40 + i, 40 * MiB + i).tobytes())
+    vm.migrate_tree(src, d1, None, shm_tmp / "t1", streams_per_gpu=1)
+    vm.migrate_tree(src, d2, None, shm_tmp / "t2")
+    assert (shm_tmp / "t1").read_bytes() == (shm_tmp / "t2").read_bytes()
+    assert orc.compare_trees(d1, d2, mtime_ns=True) == []
+
+
 def test_missing_prior_table_is_an_error(vm, shm_tmp):
     (shm_tmp / "s").mkdir(), (shm_tmp / "d").mkdir()
     (shm_tmp / "s" / "f").write_bytes(b"1" * 100)
