@@ -12,6 +12,7 @@
 #include <unistd.h>
 #include <sys/stat.h>
 #include <algorithm>
+#include <unordered_map>
 #include <thread>
 #include <cmath>
 
@@ -168,12 +169,34 @@ int run_blocks(const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior,
     uint64_t total = 0;
     for (auto& b : blocks) total += std::max<uint32_t>(b.len, 4096);
     std::vector<std::vector<BlockRef>> share(lanes);
-    {
-        uint64_t acc = 0; size_t lane = 0;
-        for (auto& b : blocks) {
-            share[lane].push_back(b);
-            acc += std::max<uint32_t>(b.len, 4096);
-            if (lane + 1 < lanes && acc >= total * (lane + 1) / lanes) lane++;
+    if (lanes == 1) {
+        share[0] = blocks;
+    } else {
+        // Prefer giving each GPU whole files (write keys): two lanes writing one destination file
+        // would queue on its inode lock.  Longest-processing-time packing of the keys by bytes; the
+        // interleaved block order is kept inside every lane.  With fewer keys than GPUs (one huge
+        // file) the list is cut into contiguous byte-balanced ranges instead.
+        std::unordered_map<uint32_t, uint64_t> key_bytes;
+        for (auto& b : blocks) key_bytes[io->write_key(b)] += std::max<uint32_t>(b.len, 4096);
+        if (key_bytes.size() >= 2 * lanes) {
+            std::vector<std::pair<uint64_t, uint32_t>> keys;
+            for (auto& kv : key_bytes) keys.push_back({kv.second, kv.first});
+            std::sort(keys.begin(), keys.end(), [](auto& a, auto& b) { return a.first != b.first ? a.first > b.first : a.second < b.second; });
+            std::vector<uint64_t> load(lanes, 0);
+            std::unordered_map<uint32_t, uint32_t> key_lane;
+            for (auto& k : keys) {
+                size_t best = 0;
+                for (size_t l = 1; l < lanes; l++) if (load[l] < load[best]) best = l;
+                load[best] += k.first; key_lane[k.second] = (uint32_t)best;
+            }
+            for (auto& b : blocks) share[key_lane[io->write_key(b)]].push_back(b);
+        } else {
+            uint64_t acc = 0; size_t lane = 0;
+            for (auto& b : blocks) {
+                share[lane].push_back(b);
+                acc += std::max<uint32_t>(b.len, 4096);
+                if (lane + 1 < lanes && acc >= total * (lane + 1) / lanes) lane++;
+            }
         }
     }
     uint32_t readers, writers;
