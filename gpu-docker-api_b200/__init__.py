@@ -42,7 +42,7 @@ EXPORTS = [
     "vmig_host_free", "vmig_hash_blocks", "vmig_resident_open", "vmig_resident_close", "vmig_resident_fill",
     "vmig_resident_set_len", "vmig_resident_upload", "vmig_resident_download", "vmig_resident_flip",
     "vmig_resident_set_prior", "vmig_resident_pass", "vmig_resident_results", "vmig_table_info_read",
-    "vmig_table_hashes", "vmig_dir_size", "vmig_to_bytes", "vmig_datagen_files",
+    "vmig_table_hashes", "vmig_dir_size", "vmig_to_bytes", "vmig_datagen_files", "vmig_manifest",
 ]
 
 
@@ -101,6 +101,7 @@ _sig = {
     "vmig_dir_size": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]),
     "vmig_to_bytes": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64)]),
     "vmig_datagen_files": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32]),
+    "vmig_manifest": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(Stats)]),
 }
 for _n, (_r, _a) in _sig.items():
     _f = getattr(_lib, _n)
@@ -327,6 +328,13 @@ class Resident:
         _check(_lib.vmig_resident_results(self.h, hashes.ctypes.data, surv.ctypes.data, C.byref(ns)),
                "vmig_resident_results")
         return hashes, surv[:ns.value].copy()
+
+
+def manifest(src, out_table=None, *, flags: int = 0, block_bytes: int = 0) -> dict:
+    """The engine's metadata pass alone (no GPU): totals, and optionally the manifest as a zero-hash table."""
+    st = Stats()
+    _check(_lib.vmig_manifest(_b(src), flags, block_bytes, _b(out_table), C.byref(st)), f"vmig_manifest({src})")
+    return st.as_dict()
 
 
 def table_info(path) -> dict:

@@ -4,6 +4,7 @@
 // BASELINE.md §3.
 #include "vmig_common.h"
 #include "vmig_table.h"
+#include "vmig_tree.h"
 
 #include <dirent.h>
 #include <fcntl.h>
@@ -63,6 +64,33 @@ int vmig_table_hashes(const char* path, uint64_t* out, uint64_t cap)
     BlockTable t; int rc = table_load(path, &t); if (rc) return rc;
     const uint64_t n = std::min<uint64_t>(cap, t.hashes.size());
     if (n) memcpy(out, t.hashes.data(), n * 8);
+    return VMIG_OK;
+}
+
+int vmig_manifest(const char* src_dir, uint32_t flags, uint32_t block_bytes, const char* out_table, vmig_stats* stats)
+{
+    if (!src_dir || !*src_dir) return fail(VMIG_EINVAL, "src_dir is NULL/empty");
+    if (!block_bytes) block_bytes = 4u << 20;
+    if (block_bytes & 4095u) return fail(VMIG_EINVAL, "block_bytes %u is not a multiple of 4096", block_bytes);
+    Manifest man;
+    const uint64_t t0 = now_ns();
+    int rc = walk_tree(src_dir, block_bytes, (flags & VMIG_F_SKIP_HIDDEN_TOPDIRS) != 0, &man);
+    if (rc) return rc;
+    if (out_table && *out_table) {
+        BlockTable t; t.block_bytes = block_bytes; t.algo = 1;
+        for (auto& e : man.files) t.files.push_back({e.rel, e.size, e.first_block});
+        t.hashes.assign(man.n_blocks, 0);
+        rc = table_store(out_table, t);
+        if (rc) return rc;
+    }
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->bytes_total = man.bytes_total; stats->blocks_total = man.n_blocks;
+        stats->files = man.files.size(); stats->dirs = man.dirs.size(); stats->symlinks = man.symlinks.size();
+        stats->specials = man.specials.size();
+        for (auto& e : man.files) if (e.hardlink_of >= 0) stats->hardlinks++;
+        stats->ns_walk = stats->ns_total = now_ns() - t0;
+    }
     return VMIG_OK;
 }
 

@@ -182,6 +182,14 @@ typedef struct vmig_table_info {
 int vmig_table_info_read(const char* path, vmig_table_info* out);
 /* Copies up to cap hashes of the table into out; returns VMIG_OK. */
 int vmig_table_hashes(const char* path, uint64_t* out, uint64_t cap);
+/* Walk src_dir exactly as vmig_migrate_tree would (same ordering, block layout, hard-link grouping,
+ * VMIG_F_SKIP_HIDDEN_TOPDIRS) and return the totals in *stats (bytes_total, blocks_total, files, dirs,
+ * symlinks, hardlinks, specials); if out_table is non-NULL also write the manifest as a block table
+ * whose hashes are all zero.  No GPU involved: this is the single metadata pass that can replace the
+ * separate DirSize walk of PatchVolumeSize's shrink check (reference internal/services/volume.go:126-140,
+ * SURVEY.md §8f N3). */
+int vmig_manifest(const char* src_dir, uint32_t flags, uint32_t block_bytes,
+                  const char* out_table /*nullable*/, vmig_stats* stats /*nullable*/);
 /* utils.DirSize (reference utils/file.go:13-22): sum of non-directory sizes under dir. */
 int vmig_dir_size(const char* dir, int64_t* bytes, uint64_t* n_files);
 /* utils.ToBytes (reference utils/file.go:24-48): "20GB" -> 21474836480; 1024-based; KB/MB/GB/TB. */

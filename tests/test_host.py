@@ -106,6 +106,33 @@ def test_block_table_reader_accepts_good_and_rejects_bad(vm, orc, shm_tmp):
         vm.table_info(shm_tmp / "gap")
 
 
+def test_manifest_pass_matches_oracle_walk(vm, orc, shm_tmp):
+    """The engine's tree walk (ordering, block layout, hard links, specials, the `mv *` quirk) against the
+    oracle's independent walk -- no GPU involved (vmig_manifest)."""
+    from conftest import make_rich_tree
+    src = shm_tmp / "src"
+    src.mkdir()
+    make_rich_tree(src, orc)
+    st = vm.manifest(src, shm_tmp / "m.vmig")
+    entries, hashes = orc.block_table_of_tree(src)
+    tab = orc.read_table(shm_tmp / "m.vmig")
+    assert tab["entries"] == entries                              # same files, sizes, first_block, bytewise order
+    assert len(tab["hashes"]) == len(hashes) and not tab["hashes"].any()
+    assert st["bytes_total"] == sum(e[1] for e in entries) and st["blocks_total"] == len(hashes)
+    assert st["files"] == len(entries) and st["symlinks"] == 2 and st["hardlinks"] == 2
+    assert st["specials"] == (2 if os.geteuid() == 0 else 1)      # fifo (+ whiteout char device as root)
+    n_dirs = 1 + sum(len(d) for _, d, _ in os.walk(src))
+    assert st["dirs"] == n_dirs
+    # DirSize (utils/file.go:13-22) counts every non-directory's st_size; the manifest counts regular files
+    assert vm.DirSize(str(src)) >= st["bytes_total"]
+    # the reference's `mv /root/src/*` leaves top-level hidden directories behind
+    st2 = vm.manifest(src, shm_tmp / "m2.vmig", flags=vm.F_SKIP_HIDDEN_TOPDIRS)
+    assert st2["files"] == st["files"] - 1 and st2["dirs"] == st["dirs"] - 1
+    assert all(not e[0].startswith(b".hidden_dir/") for e in orc.read_table(shm_tmp / "m2.vmig")["entries"])
+    with pytest.raises(vm.VmigError):
+        vm.manifest(shm_tmp / "nope")
+
+
 def test_reference_interface_resolvers(vm):
     vm.set_resolver(None, None)
     with pytest.raises(vm.VmigError):
