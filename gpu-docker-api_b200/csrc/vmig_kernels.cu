@@ -297,8 +297,9 @@ xxh64_blocks_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict
 #pragma unroll
                 for (int o = 16; o >= 1; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
             }
+            __syncwarp();                                  // the leaders' descriptor stores precede lane 0's (releasing) arrive
             if (lane == 0) { if (tot) mbar_arrive_expect_tx(bar, tot); else mbar_arrive(bar); }
-            __syncwarp();
+            __syncwarp();                                  // ... and the expect_tx precedes every bulk copy of the stage
             if (leader && nb) bulk_g2s(data_s + stage * kStageStride + quad * kQuadStride, base + iss_off, nb, bar);
             if (!iss_done) {
                 iss_off += nb; iss_rem -= nb; iss_first = false;
