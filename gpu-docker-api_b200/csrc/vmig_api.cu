@@ -201,9 +201,9 @@ int run_blocks(const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior,
     }
     uint32_t readers, writers;
     {
-        uint32_t distinct = 0, last = 0xFFFFFFFFu;               // blocks are interleaved across <= 64 files
-        for (size_t i = 0; i < blocks.size() && i < 256 && distinct < 32; i++) if (blocks[i].file != last) { distinct++; last = blocks[i].file; }
-        io_threads_default(&readers, &writers, o.io_threads, lanes, distinct >= 32);
+        std::unordered_map<uint32_t, int> seen;                  // blocks are interleaved across <= 64 files
+        for (size_t i = 0; i < blocks.size() && i < 256; i++) seen[io->write_key(blocks[i])] = 1;
+        io_threads_default(&readers, &writers, o.io_threads, lanes, seen.size() >= 32);
     }
     std::vector<Pipe*> pipes(lanes, nullptr);
     for (size_t i = 0; i < lanes; i++) {
