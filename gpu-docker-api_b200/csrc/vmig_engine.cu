@@ -91,6 +91,7 @@ static int ring_alloc(uint8_t** out, size_t bytes, size_t* mapped)
             const size_t tail = (size_t)(((uint8_t*)p + len + (2u << 20)) - (a + len));
             if (tail) munmap(a + len, tail);
             madvise(a, len, MADV_HUGEPAGE);
+            madvise(a, len, MADV_DONTFORK);        // a forked child (the control plane exec's tools) must not share DMA targets
             memset(a, 0, len);
             if (cudaHostRegister(a, len, cudaHostRegisterPortable) == cudaSuccess) { *out = a; *mapped = len; return VMIG_OK; }
             cudaGetLastError();
