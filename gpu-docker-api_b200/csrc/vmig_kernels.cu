@@ -312,7 +312,7 @@ xxh64_blocks_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict
         for (uint32_t rf = 0;; rf++) {
             if (__all_sync(0xFFFFFFFFu, iss_done)) break;      // an all-NONE stage is out: everyone stops there
             const int stage = rf % kStages;
-            while (lds_volatile(done_cnt_s) <= rf) __nanosleep(20);            // the chains drained chunk rf
+            while (lds_volatile(done_cnt_s) <= rf) __nanosleep(200);           // the chains drained chunk rf (a poll every ~400 cycles: the ring has 6 stages of slack, the chain warp's scheduler has none)
             K1_TRACE(0, rf + kStages, 0);
             issue(stage);                                                      // chunk rf + kStages
             K1_TRACE(0, rf + kStages, 1);

@@ -69,7 +69,7 @@ const char* vmig_version(void);
 /* ---- options / statistics ------------------------------------------------------------------ */
 #define VMIG_F_MOVE_SRC          0x01u  /* unlink source entries after a verified copy: the `mv` of
                                            moveVolumeData (reference utils/copy.go:116)            */
-#define VMIG_F_SKIP_HIDDEN_TOPDIRS 0x02u /* reproduce `mv /root/src/*`: top-level hidden DIRECTORIES
+#define VMIG_F_SKIP_HIDDEN_TOPDIRS 0x02u /* reproduce `mv /root/src/ *`: top-level hidden DIRECTORIES
                                            are left behind (reference utils/copy.go:116)           */
 #define VMIG_F_MTIME_NS          0x04u  /* keep nanosecond mtimes (mv does; GNU tar's default archive
                                            format keeps whole seconds only -> default off)         */
