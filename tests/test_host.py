@@ -33,6 +33,24 @@ def test_library_exports_every_declared_symbol(vm):
     assert "sm_100a" in vm.version()
 
 
+def test_c_abi_from_plain_c(vm, shm_tmp):
+    """include/vmig.h is plain C and the library links from C the way cgo would link it."""
+    import subprocess
+    exe = shm_tmp / "c_abi_smoke"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(ROOT / "tests" / "c_abi_smoke.c"),
+                    "-o", str(exe), str(vm.LIB_PATH), "-Wl,-rpath," + str(vm.LIB_PATH.parent)], check=True)
+    src, dst = shm_tmp / "s", shm_tmp / "d"
+    (src / "sub").mkdir(parents=True), dst.mkdir()
+    (src / "a").write_bytes(b"x" * 5000), (src / "sub" / "b").write_bytes(b"y" * 70)
+    r = subprocess.run([str(exe), str(src), str(dst)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "files=2 bytes=5070 dir_size=5070" in r.stdout
+    if "copy ok" in r.stdout:
+        assert (dst / "sub" / "b").read_bytes() == b"y" * 70
+    else:
+        assert "no CPU fallback" in r.stdout and os.listdir(dst) == []
+
+
 def test_struct_layouts_match_header(vm):
     assert ctypes.sizeof(vm.Opts) == 32
     assert ctypes.sizeof(vm.Stats) == 18 * 8 + 8 + 8
