@@ -261,9 +261,55 @@ template <> __device__ __forceinline__ void run<16>(uint32_t& a, uint32_t& b, ui
     a = tlo; b = thi;
 }
 
+
+// V17/V18: no helper warp -- the chain warp pre-multiplies its own input G rounds ahead (raw x read from shared
+// memory with volatile loads so the products cannot be hoisted), V15's chain on the result.  The x*P2 work is
+// independent of the chain, so it should fill the chain's stall slots; both share the FMA pipe
+// (2 x IMAD.WIDE + 4 x IMAD per round = ~22.8 pipe cycles against a 23.9-cycle dependent path).
+__device__ __forceinline__ void premulP2(uint64_t x, uint32_t& ml, uint32_t& mh) {
+    const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32);
+    uint32_t hi;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(ml) : "r"(xl), "r"(P2lo));
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(xl), "r"(P2lo));
+    asm("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %1, %3, %5;\n\tmad.lo.u32 %0, %2, %4, a;\n\t}" : "=r"(mh) : "r"(xl), "r"(xh), "r"(P2hi), "r"(P2lo), "r"(hi));
+}
+__device__ __forceinline__ void round15(uint32_t& tlo, uint32_t& thi, uint32_t ml, uint32_t mhh) {
+    const uint32_t rl = __funnelshift_l(thi, tlo, 31), rh = __funnelshift_l(tlo, thi, 31);
+    uint32_t lo, hi, mhv;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(lo) : "r"(rl), "r"(P1lo));
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(rl), "r"(P1lo));
+    asm("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %2, %3, %5;\n\tmad.lo.u32 %0, %1, %4, a;\n\t}" : "=r"(mhv) : "r"(rl), "r"(rh), "r"(P1lo), "r"(P1hi), "r"(mhh));
+    asm("{\n\tadd.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;\n\t}" : "=r"(tlo), "=r"(thi) : "r"(lo), "r"(ml), "r"(hi), "r"(mhv));
+}
+template <int G> __device__ __forceinline__ void run_inwarp(uint32_t& a, uint32_t& b, const uint64_t* xs) {
+    const volatile uint64_t* vx = xs + (threadIdx.x & 15);   // per-lane addresses: keep it off the uniform datapath
+    uint32_t tlo = a, thi = b, ml[G], mh[G];
+    uint64_t xr[G];                                   // raw words of the NEXT group, loaded one group early
+#pragma unroll
+    for (int j = 0; j < G; j++) premulP2(vx[j], ml[j], mh[j]);
+#pragma unroll
+    for (int j = 0; j < G; j++) xr[j] = vx[(G + j) & 15];
+#pragma unroll 1
+    for (int i = 0; i < N; i += G) {
+        uint32_t nl[G], nh[G]; uint64_t xn[G];
+#pragma unroll
+        for (int j = 0; j < G; j++) xn[j] = vx[(i + 2 * G + j) & 15];
+#pragma unroll
+        for (int j = 0; j < G; j++) {
+            premulP2(xr[j], nl[j], nh[j]);
+            round15(tlo, thi, ml[j], mh[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < G; j++) { ml[j] = nl[j]; mh[j] = nh[j]; xr[j] = xn[j]; }
+    }
+    a = tlo; b = thi;
+}
+template <> __device__ __forceinline__ void run<17>(uint32_t& a, uint32_t& b, uint32_t& c, const uint64_t* xs) { run_inwarp<4>(a, b, xs); }
+template <> __device__ __forceinline__ void run<18>(uint32_t& a, uint32_t& b, uint32_t& c, const uint64_t* xs) { run_inwarp<8>(a, b, xs); }
+
 template <int V> __global__ void k(uint32_t* out, long long* cyc, uint32_t seed) {
-    __shared__ uint64_t xs[16];
-    if (threadIdx.x < 16) xs[threadIdx.x] = 0x9E3779B97F4A7C15ULL * (threadIdx.x + seed);
+    __shared__ uint64_t xs[32];
+    if (threadIdx.x < 32) xs[threadIdx.x] = 0x9E3779B97F4A7C15ULL * (threadIdx.x + seed);
     __syncthreads();
     uint32_t a = threadIdx.x + seed, b = seed * 3 + 1, c = seed * 7 + 5;
     long long t0 = clock64();
@@ -301,6 +347,8 @@ int main() {
     go<14>("XXH64 round, m preloaded, IMAD+IMAD.HI+pred carry", 1, out, cyc);
     go<15>("XXH64 round, m preloaded, mul.lo/hi + add.cc", 1, out, cyc);
     go<16>("XXH64 round, m preloaded, IMAD.HI + IMAD(reg) + add.cc", 1, out, cyc);
+    go<17>("XXH64 round, in-warp premul 4 rounds ahead + V15", 1, out, cyc);
+    go<18>("XXH64 round, in-warp premul 8 rounds ahead + V15", 1, out, cyc);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }

@@ -203,7 +203,7 @@ int run_blocks(const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior,
     {
         std::unordered_map<uint32_t, int> seen;                  // blocks are interleaved across <= 64 files
         for (size_t i = 0; i < blocks.size() && i < 256; i++) seen[io->write_key(blocks[i])] = 1;
-        io_threads_default(&readers, &writers, o.io_threads, lanes, seen.size() >= 32);
+        io_threads_default(&readers, &writers, o.io_threads, lanes, seen.size() >= 32, has_prior, hash_only);
     }
     std::vector<Pipe*> pipes(lanes, nullptr);
     for (size_t i = 0; i < lanes; i++) {
