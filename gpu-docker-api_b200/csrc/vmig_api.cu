@@ -506,13 +506,11 @@ struct vmig_resident {
 
 #define CU_API(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cudaGetLastError(); return fail(e__ == cudaErrorMemoryAllocation ? VMIG_ENOMEM : VMIG_ECUDA, "%s: %s", #call, cudaGetErrorString(e__)); } } while (0)
 
-int vmig_resident_open(int gpu, uint64_t n_blocks, uint32_t block_bytes, vmig_resident** out)
+void vmig_resident_close(vmig_resident* r);
+
+static int resident_alloc(vmig_resident* r, uint64_t n_blocks, uint32_t block_bytes)
 {
-    if (!out || !n_blocks || !block_bytes || (block_bytes & 511u) || n_blocks > 0x7FFFFFFFull) return fail(VMIG_EINVAL, "bad resident geometry");
-    std::vector<DeviceInfo> devs; int rc = ctx_select(1u << gpu, &devs); if (rc) return rc;
-    vmig_resident* r = new vmig_resident(); memset(r, 0, sizeof *r);
-    r->dev = gpu; r->sm_count = devs[0].sm_count; r->n = n_blocks; r->block_bytes = block_bytes;
-    CU_API(cudaSetDevice(gpu));
+    CU_API(cudaSetDevice(r->dev));
     CU_API(cudaMalloc((void**)&r->d_data, n_blocks * (uint64_t)block_bytes + kTailPad));
     CU_API(cudaMalloc((void**)&r->d_offs, n_blocks * 8)); CU_API(cudaMalloc((void**)&r->d_lens, n_blocks * 4));
     CU_API(cudaMalloc((void**)&r->d_hashes, n_blocks * 8)); CU_API(cudaMalloc((void**)&r->d_prior, n_blocks * 8));
@@ -527,6 +525,23 @@ int vmig_resident_open(int gpu, uint64_t n_blocks, uint32_t block_bytes, vmig_re
     CU_API(cudaMemcpy(r->d_lens, lens.data(), n_blocks * 4, cudaMemcpyHostToDevice));
     CU_API(cudaMemset(r->d_valid, 0, n_blocks)); CU_API(cudaMemset(r->d_prior, 0, n_blocks * 8));
     CU_API(cudaMemset(r->d_data + n_blocks * (uint64_t)block_bytes, 0, kTailPad));
+    return VMIG_OK;
+}
+
+int vmig_resident_open(int gpu, uint64_t n_blocks, uint32_t block_bytes, vmig_resident** out)
+{
+    if (!out || !n_blocks || !block_bytes || (block_bytes & 511u) || n_blocks > 0x7FFFFFFFull) return fail(VMIG_EINVAL, "bad resident geometry");
+    if (gpu < 0 || gpu > 31) return fail(VMIG_EINVAL, "bad gpu index %d", gpu);
+    std::vector<DeviceInfo> devs; int rc = ctx_select(1u << gpu, &devs); if (rc) return rc;
+    vmig_resident* r = new vmig_resident(); memset(r, 0, sizeof *r);
+    r->dev = gpu; r->sm_count = devs[0].sm_count; r->n = n_blocks; r->block_bytes = block_bytes;
+    rc = resident_alloc(r, n_blocks, block_bytes);
+    if (rc) {                                   // e.g. the batch does not fit in HBM: give back what was taken
+        const std::string keep = last_error_cstr();
+        vmig_resident_close(r);
+        set_last_error_str(keep);
+        return rc;
+    }
     *out = r;
     return VMIG_OK;
 }

@@ -86,6 +86,24 @@ def test_k1_rejects_block_larger_than_slot(vm):
 
 
 # ------------------------------------------------------------------------------------ resident
+def test_resident_open_that_does_not_fit_fails_cleanly(vm):
+    """A batch larger than HBM is refused with VMIG_ENOMEM and leaves nothing behind: a normal batch
+    opens right after it (the partial allocation was given back)."""
+    with pytest.raises(vm.VmigError) as ei:
+        vm.Resident(100_000, 4 * MiB)                 # 400 GB > 180 GB of HBM
+    assert ei.value.code == vm.VMIG_ENOMEM
+    with pytest.raises(vm.VmigError) as ei:
+        vm.Resident(4, 4 * MiB, gpu=77)
+    assert ei.value.code in (vm.VMIG_EINVAL, vm.VMIG_ENOGPU)
+    r = vm.Resident(64, 4 * MiB)
+    try:
+        r.fill(1); r.set_prior(None); r.run(1)
+        h, surv = r.results()
+        assert len(surv) == 64 and len(set(h.tolist())) == 64
+    finally:
+        r.close()
+
+
 def test_resident_fill_hash_diff_select(vm, orc):
     """HBM-resident pass: device generator == oracle generator, hashes == oracle on sampled
     blocks, and diff_select returns exactly the flipped / invalid-prior blocks, ascending."""
