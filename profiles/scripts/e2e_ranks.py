@@ -2,7 +2,8 @@
 torchrun: used to study how the host side scales.  Environment knobs (VMIG_*) pass through to every rank.
 usage: python profiles/scripts/e2e_ranks.py N [steps=3] [n_files=10] [mode=copy]
 mode: copy (vmig_migrate_tree) | hash (VMIG_F_HASH_ONLY: read side + H2D only) | buffer (pinned -> pinned,
-no file I/O) | tar (the reference's pipe, no GPU) | mount (copy, each rank on its own tmpfs mount)"""
+no file I/O) | tar (the reference's pipe, no GPU) | mount (copy, each rank on its own tmpfs mount)
+VMIG_SWEEP="8:12,5:8,3:5" repeats the timed steps for each readers:writers pair on the same trees."""
 import multiprocessing as mp, os, shutil, sys, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[2]
@@ -25,7 +26,10 @@ def rank_main(rank, world, steps, n_files, bar, out, mode):
         a.array[:] = 7; b.array[:] = 0
     else:
         vm.datagen_files(base / "src", 2 + 1000 * rank, n_files, 1 << 30, threads=max(4, 64 // world))
-    for i in range(steps + 1):
+    sweep = [x for x in os.environ.get("VMIG_SWEEP", "").split(",") if x] or [None]
+    for i in range((steps + 1) * len(sweep)):
+        cfg = sweep[i // (steps + 1)]
+        if cfg: os.environ["VMIG_READERS"], os.environ["VMIG_WRITERS"] = cfg.split(":")
         shutil.rmtree(base / "dst", ignore_errors=True); (base / "dst").mkdir()
         bar.wait()
         t0 = time.perf_counter()
@@ -35,7 +39,7 @@ def rank_main(rank, world, steps, n_files, bar, out, mode):
         elif mode == "tar": subprocess.run(["sh", "-c", f"(cd {base}/src; tar c .) | (cd {base}/dst; tar x)"], check=True)
         dt = time.perf_counter() - t0
         bar.wait()
-        if i: times.append(dt)
+        if i % (steps + 1): times.append(dt)
     out.put((rank, times))
     if mode == "mount": subprocess.run(["umount", str(base)])
     else: shutil.rmtree(base, ignore_errors=True)
@@ -50,8 +54,11 @@ if __name__ == "__main__":
     [p.start() for p in ps]
     res = dict(out.get() for _ in ps)
     [p.join() for p in ps]
-    worst = [max(res[r][i] for r in res) for i in range(steps)]
-    knobs = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("VMIG_"))
-    print(f"N={world} {mode} [{knobs}] per-step max-over-ranks ms: {[round(1e3 * t) for t in worst]}  -> "
-          f"{world * n_files * steps / sum(worst):.2f} GiB/s total; per-rank mean ms: "
-          f"{[round(1e3 * sum(res[r]) / steps) for r in sorted(res)]}", flush=True)
+    knobs = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("VMIG_") and k != "VMIG_SWEEP")
+    sweep = [x for x in os.environ.get("VMIG_SWEEP", "").split(",") if x] or [None]
+    for ci, cfg in enumerate(sweep):
+        sl = slice(ci * steps, (ci + 1) * steps)
+        worst = [max(res[r][sl][i] for r in res) for i in range(steps)]
+        print(f"N={world} {mode} [{knobs}{' R:W=' + cfg if cfg else ''}] per-step max-over-ranks ms: {[round(1e3 * t) for t in worst]}  -> "
+              f"{world * n_files * steps / sum(worst):.2f} GiB/s total; per-rank mean ms: "
+              f"{[round(1e3 * sum(res[r][sl]) / steps) for r in sorted(res)]}", flush=True)
