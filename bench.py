@@ -200,6 +200,9 @@ def main() -> None:
     import __graft_entry__ as g
     vm = g.load_pkg()
     gpu = local if world > 1 else 0
+    if world > 1:
+        # one process per GPU: tell each rank's engine how many migrations share the host's copy threads
+        os.environ.setdefault("VMIG_IO_SHARE", str(world))
     vm.init(1 << gpu)                       # fails loudly without a B200: no CPU fallback
     n_blocks = N_FILES * FILE_BYTES // BLOCK
     nbytes = N_FILES * FILE_BYTES

@@ -280,6 +280,8 @@ int ctx_select(uint32_t mask, std::vector<DeviceInfo>* out)
     return VMIG_OK;
 }
 
+static std::atomic<long> g_active_lanes{0};     // pipes checked out by calls in flight in this process
+
 int ctx_acquire_pipe(const DeviceInfo& d, Pipe** out)
 {
     std::unique_lock<std::mutex> lk(g_mu);
@@ -287,7 +289,7 @@ int ctx_acquire_pipe(const DeviceInfo& d, Pipe** out)
         DevPool* dp = nullptr;
         for (auto& x : g_devs) if (x.info.dev == d.dev) dp = &x;
         if (!dp) return fail(VMIG_ENOGPU, "device %d not initialised", d.dev);
-        if (!dp->free_pipes.empty()) { *out = dp->free_pipes.back(); dp->free_pipes.pop_back(); return VMIG_OK; }
+        if (!dp->free_pipes.empty()) { *out = dp->free_pipes.back(); dp->free_pipes.pop_back(); g_active_lanes++; return VMIG_OK; }
         if (dp->n_pipes < g_pipes_per_gpu) {
             dp->n_pipes++;
             lk.unlock();
@@ -301,6 +303,7 @@ int ctx_acquire_pipe(const DeviceInfo& d, Pipe** out)
                 return rc;
             }
             *out = p;
+            g_active_lanes++;
             return VMIG_OK;
         }
         g_cv.wait(lk);
@@ -308,6 +311,7 @@ int ctx_acquire_pipe(const DeviceInfo& d, Pipe** out)
 }
 void ctx_release_pipe(Pipe* p)
 {
+    g_active_lanes--;
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto& x : g_devs) if (x.info.dev == p->dev.dev) { x.free_pipes.push_back(p); g_cv.notify_all(); return; }
     p->destroy(); delete p;    // context was shut down underneath us
@@ -321,8 +325,10 @@ int io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested,
     if (r <= 0 || w <= 0) {
         cpu_set_t cur; CPU_ZERO(&cur);
         long ncpu = sched_getaffinity(0, sizeof cur, &cur) == 0 ? CPU_COUNT(&cur) : sysconf(_SC_NPROCESSORS_ONLN);
-        int ngpu = 1; if (cudaGetDeviceCount(&ngpu) != cudaSuccess) { cudaGetLastError(); ngpu = 1; }
-        long share = std::max<long>(lanes, (size_t)ngpu);         // other GPUs may be busy migrating too
+        // the host's copy capacity is shared by every migration running on it: this call's lanes, the
+        // lanes of other calls in flight in this process, and -- when the deployment runs one process per
+        // GPU, as bench.py under torchrun does -- whatever VMIG_IO_SHARE says (migrations expected at once)
+        long share = std::max<long>((long)lanes + std::max<long>(0, g_active_lanes.load()), env_long("VMIG_IO_SHARE", 1));
         // measured on the 2-socket bench box (profiles/r01_e2e_threads.txt): the copy threads are
         // memory-bound, more of them than ~8 readers + ~12 writers per GPU only adds contention
         long budget = std::min<long>(24, std::max<long>(4, ncpu / share));

@@ -12,6 +12,7 @@ def rank_main(rank, world, steps, n_files, bar, out, mode):
     sys.path.insert(0, str(ROOT))
     import __graft_entry__ as g
     vm = g.load_pkg()
+    os.environ.setdefault("VMIG_IO_SHARE", str(world))
     vm.init(1 << rank)
     import subprocess
     base = Path(f"/dev/shm/vmig_ranks_r{rank}")
