@@ -33,6 +33,7 @@ public:
         uint64_t dst_old_size = 0;
     };
     std::string src_root, dst_root;
+    int src_root_fd = -1;                // source files are opened beneath this descriptor, never by absolute path
     const Manifest* m = nullptr;
     MetaPolicy pol;
     bool hash_only = false;
@@ -47,9 +48,15 @@ public:
             std::lock_guard<std::mutex> lk(stripes[f & 63]);
             fd = s.sfd.load(std::memory_order_acquire);
             if (fd < 0) {
-                const std::string p = pjoin(src_root, m->files[f].rel);
-                fd = open(p.c_str(), O_RDONLY | O_CLOEXEC | O_NOFOLLOW);
-                if (fd < 0) return fail(VMIG_EIO, "open %s: %s", p.c_str(), errno_str(errno).c_str());
+                // the tenant may still be running on this layer: no symlink is followed and the root is never
+                // left (vmig_tree.h open_beneath); O_NONBLOCK so a FIFO swapped in cannot park a reader thread
+                int rc = open_beneath(src_root_fd, m->files[f].rel, O_RDONLY | O_NONBLOCK, &fd);
+                if (rc) return rc;
+                struct stat st;
+                if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+                    close(fd);
+                    return fail(VMIG_ESRCCHANGED, "%s is not a regular file any more", m->files[f].rel.c_str());
+                }
                 s.sfd.store(fd, std::memory_order_release);
             }
         }
@@ -128,6 +135,12 @@ public:
         s.dfd.store(-1);
         return rc;
     }
+    int open_root() {
+        src_root_fd = open(src_root.c_str(), O_RDONLY | O_DIRECTORY | O_CLOEXEC);
+        if (src_root_fd < 0) return fail(VMIG_EIO, "open %s: %s", src_root.c_str(), errno_str(errno).c_str());
+        return VMIG_OK;
+    }
+    ~FileIO() { if (src_root_fd >= 0) close(src_root_fd); }
     void close_all(size_t n) {
         for (size_t i = 0; i < n; i++) {
             int a = fs[i].sfd.exchange(-1); if (a >= 0) close(a);
@@ -276,6 +289,7 @@ int migrate_tree_impl(const char* src_dir, const char* dst_dir, const char* prio
     FileIO io;
     io.src_root = src; io.dst_root = dst; io.m = &man; io.pol = default_meta_policy(o.flags); io.hash_only = hash_only;
     io.corrupt_block = env_long("VMIG_CORRUPT_BLOCK", -1);
+    rc = io.open_root(); if (rc) return rc;
     io.fs.reset(new FileIO::FS[man.files.size() ? man.files.size() : 1]);
     std::vector<uint64_t> hashes(man.n_blocks, 0);
 
@@ -357,6 +371,7 @@ int migrate_tree_impl(const char* src_dir, const char* dst_dir, const char* prio
         FileIO vio;
         vio.src_root = dst; vio.dst_root = dst; vio.m = &man; vio.pol = io.pol; vio.hash_only = true;
         vio.fs.reset(new FileIO::FS[man.files.size() ? man.files.size() : 1]);
+        rc = vio.open_root(); if (rc) return rc;
         for (uint32_t f = 0; f < man.files.size(); f++) {
             const Entry& e = man.files[f];
             if (e.hardlink_of >= 0 || e.n_blocks == 0) continue;

@@ -5,8 +5,11 @@
 #include <dirent.h>
 #include <fcntl.h>
 #include <unistd.h>
+#include <linux/openat2.h>
+#include <sys/syscall.h>
 #include <sys/sysmacros.h>
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <utility>
 
@@ -17,12 +20,63 @@ static inline std::string join(const std::string& a, const std::string& b) {
     return a + "/" + b;
 }
 
-static int walk_dir(const std::string& root, const std::string& rel, uint32_t block_bytes, bool skip_hidden_topdirs,
+// The source may belong to a container that is still running (the first pass of a two-pass hand-off), so
+// nothing on the source side trusts a path twice: directories are entered with openat(O_NOFOLLOW) relative to
+// their parent's descriptor, and files are opened later with open_beneath() below.  A directory that a tenant
+// swaps for a symlink between the lstat and the open makes the call fail; it is never followed out of the tree
+// (GNU tar walks the same way, which is what the reference's `tar c .` relies on).
+int open_beneath(int root_fd, const std::string& rel, int flags, int* out_fd)
+{
+    static std::atomic<int> have_openat2{1};
+    if (rel.empty() || rel[0] == '/') return fail(VMIG_EINVAL, "open_beneath: bad relative path '%s'", rel.c_str());
+    if (have_openat2.load(std::memory_order_relaxed)) {
+        struct open_how how; memset(&how, 0, sizeof how);
+        how.flags = (uint64_t)(flags | O_CLOEXEC | O_NOFOLLOW);
+        how.resolve = RESOLVE_BENEATH | RESOLVE_NO_SYMLINKS | RESOLVE_NO_MAGICLINKS;
+        long fd = syscall(SYS_openat2, root_fd, rel.c_str(), &how, sizeof how);
+        if (fd >= 0) { *out_fd = (int)fd; return VMIG_OK; }
+        if (errno != ENOSYS) {
+            const int e = errno;
+            if (e == ELOOP || e == EXDEV || e == ENOTDIR)
+                return fail(VMIG_ESRCCHANGED, "%s is no longer a plain path beneath the source root (%s): a symlink or rename raced the walk", rel.c_str(), errno_str(e).c_str());
+            return fail(e == ENOENT ? VMIG_ESRCCHANGED : VMIG_EIO, "open %s: %s", rel.c_str(), errno_str(e).c_str());
+        }
+        have_openat2.store(0, std::memory_order_relaxed);      // pre-5.6 kernel: walk the components by hand
+    }
+    return open_beneath_walk(root_fd, rel, flags, out_fd);
+}
+
+int open_beneath_walk(int root_fd, const std::string& rel, int flags, int* out_fd)
+{
+    if (rel.empty() || rel[0] == '/') return fail(VMIG_EINVAL, "open_beneath: bad relative path '%s'", rel.c_str());
+    int cur = root_fd; bool own = false;
+    size_t pos = 0;
+    for (;;) {
+        const size_t slash = rel.find('/', pos);
+        const std::string comp = rel.substr(pos, slash == std::string::npos ? std::string::npos : slash - pos);
+        const bool last = slash == std::string::npos;
+        if (comp.empty() || comp == "." || comp == "..") { if (own) close(cur); return fail(VMIG_EINVAL, "open_beneath: bad component in '%s'", rel.c_str()); }
+        const int fl = last ? (flags | O_CLOEXEC | O_NOFOLLOW) : (O_RDONLY | O_DIRECTORY | O_CLOEXEC | O_NOFOLLOW);
+        const int fd = openat(cur, comp.c_str(), fl);
+        const int e = errno;
+        if (own) close(cur);
+        if (fd < 0) {
+            if (e == ELOOP || e == ENOTDIR || e == ENOENT)
+                return fail(VMIG_ESRCCHANGED, "%s is no longer a plain path beneath the source root (%s)", rel.c_str(), errno_str(e).c_str());
+            return fail(VMIG_EIO, "open %s: %s", rel.c_str(), errno_str(e).c_str());
+        }
+        if (last) { *out_fd = fd; return VMIG_OK; }
+        cur = fd; own = true; pos = slash + 1;
+    }
+}
+
+// dfd: open descriptor of the directory `rel`; consumed (closed) by this call.
+static int walk_dir(int dfd, const std::string& rel, uint32_t block_bytes, bool skip_hidden_topdirs,
                     Manifest* m, std::map<std::pair<dev_t, ino_t>, std::string>* inode_first, int depth)
 {
-    const std::string abs = join(root, rel);
-    DIR* d = opendir(abs.c_str());
-    if (!d) return fail(VMIG_EIO, "opendir %s: %s", abs.c_str(), errno_str(errno).c_str());
+    const int dfd_dup = dup(dfd);
+    DIR* d = dfd_dup >= 0 ? fdopendir(dfd) : nullptr;
+    if (!d) { const int e = errno; close(dfd); if (dfd_dup >= 0) close(dfd_dup); return fail(VMIG_EIO, "opendir %s: %s", rel.c_str(), errno_str(e).c_str()); }
     std::vector<std::string> names;
     errno = 0;
     while (struct dirent* de = readdir(d)) {
@@ -31,18 +85,16 @@ static int walk_dir(const std::string& root, const std::string& rel, uint32_t bl
         names.emplace_back(n);
     }
     const int rd_errno = errno;
-    const int dfd_dup = dup(dirfd(d));
-    closedir(d);
-    if (rd_errno) { if (dfd_dup >= 0) close(dfd_dup); return fail(VMIG_EIO, "readdir %s: %s", abs.c_str(), errno_str(rd_errno).c_str()); }
-    if (dfd_dup < 0) return fail(VMIG_EIO, "dup dirfd %s: %s", abs.c_str(), errno_str(errno).c_str());
+    closedir(d);                                   // closes dfd; dfd_dup stays for the *at() calls
+    if (rd_errno) { close(dfd_dup); return fail(VMIG_EIO, "readdir %s: %s", rel.c_str(), errno_str(rd_errno).c_str()); }
     std::sort(names.begin(), names.end());
 
-    std::vector<std::string> subdirs;
+    std::vector<std::pair<std::string, std::string>> subdirs;     // (name, rel)
     for (const auto& n : names) {
         struct stat st;
         if (fstatat(dfd_dup, n.c_str(), &st, AT_SYMLINK_NOFOLLOW) != 0) {
             const int e = errno; close(dfd_dup);
-            return fail(VMIG_EIO, "lstat %s/%s: %s", abs.c_str(), n.c_str(), errno_str(e).c_str());
+            return fail(VMIG_EIO, "lstat %s/%s: %s", rel.c_str(), n.c_str(), errno_str(e).c_str());
         }
         Entry e;
         e.rel = rel == "." ? n : rel + "/" + n;
@@ -50,7 +102,7 @@ static int walk_dir(const std::string& root, const std::string& rel, uint32_t bl
         switch (st.st_mode & S_IFMT) {
         case S_IFDIR:
             if (skip_hidden_topdirs && depth == 0 && n[0] == '.') continue;   // `mv /root/src/*` misses these
-            e.type = kDir; m->dirs.push_back(e); subdirs.push_back(e.rel);
+            e.type = kDir; m->dirs.push_back(e); subdirs.push_back({n, e.rel});
             break;
         case S_IFREG: {
             e.type = kFile; e.size = (uint64_t)st.st_size;
@@ -82,11 +134,18 @@ static int walk_dir(const std::string& root, const std::string& rel, uint32_t bl
         default: break;
         }
     }
-    close(dfd_dup);
-    for (const auto& s : subdirs) {
-        int rc = walk_dir(root, s, block_bytes, skip_hidden_topdirs, m, inode_first, depth + 1);
-        if (rc) return rc;
+    for (const auto& sd : subdirs) {
+        const int cfd = openat(dfd_dup, sd.first.c_str(), O_RDONLY | O_DIRECTORY | O_NOFOLLOW | O_CLOEXEC);
+        if (cfd < 0) {
+            const int e = errno; close(dfd_dup);
+            return fail(e == ELOOP || e == ENOTDIR || e == ENOENT ? VMIG_ESRCCHANGED : VMIG_EIO,
+                        "open directory %s: %s%s", sd.second.c_str(), errno_str(e).c_str(),
+                        e == ELOOP || e == ENOTDIR ? " (it was a directory a moment ago: not following)" : "");
+        }
+        int rc = walk_dir(cfd, sd.second, block_bytes, skip_hidden_topdirs, m, inode_first, depth + 1);
+        if (rc) { close(dfd_dup); return rc; }
     }
+    close(dfd_dup);
     return VMIG_OK;
 }
 
@@ -101,7 +160,9 @@ int walk_tree(const std::string& src_root, uint32_t block_bytes, bool skip_hidde
     root.mtime = st.st_mtim; root.atime = st.st_atim;
     m->dirs.push_back(root);
     std::map<std::pair<dev_t, ino_t>, std::string> inode_first;
-    int rc = walk_dir(src_root, ".", block_bytes, skip_hidden_topdirs, m, &inode_first, 0);
+    const int rfd = open(src_root.c_str(), O_RDONLY | O_DIRECTORY | O_CLOEXEC);
+    if (rfd < 0) return fail(VMIG_EIO, "open %s: %s", src_root.c_str(), errno_str(errno).c_str());
+    int rc = walk_dir(rfd, ".", block_bytes, skip_hidden_topdirs, m, &inode_first, 0);
     if (rc) return rc;
 
     std::sort(m->files.begin(), m->files.end(), [](const Entry& a, const Entry& b) { return a.rel < b.rel; });
@@ -251,21 +312,43 @@ int replay_metadata(const std::string& dst_root, const Manifest& m, const MetaPo
 
 int remove_source(const std::string& src_root, const Manifest& m)
 {
+    // unlinkat() relative to the entry's parent directory, itself re-opened beneath the root without following
+    // symlinks: a path swapped under us can make the call fail, not delete something outside the tree
+    const int rfd = open(src_root.c_str(), O_RDONLY | O_DIRECTORY | O_CLOEXEC);
+    if (rfd < 0) return fail(VMIG_EIO, "open %s: %s", src_root.c_str(), errno_str(errno).c_str());
+    std::string cur_parent = "\x01"; int pfd = -1;
+    auto parent_of = [&](const std::string& rel, std::string* base) -> int {
+        const size_t slash = rel.rfind('/');
+        const std::string parent = slash == std::string::npos ? "." : rel.substr(0, slash);
+        *base = slash == std::string::npos ? rel : rel.substr(slash + 1);
+        if (parent == cur_parent) return VMIG_OK;
+        if (pfd >= 0 && pfd != rfd) close(pfd);
+        pfd = -1; cur_parent = "\x01";
+        if (parent == ".") pfd = rfd;
+        else { int rc = open_beneath(rfd, parent, O_RDONLY | O_DIRECTORY, &pfd); if (rc) return rc; }
+        cur_parent = parent;
+        return VMIG_OK;
+    };
+    auto finish = [&](int rc) { if (pfd >= 0 && pfd != rfd) close(pfd); close(rfd); return rc; };
     auto rm = [&](const std::vector<Entry>& v) -> int {
         for (const auto& e : v) {
-            const std::string p = join(src_root, e.rel);
-            if (unlink(p.c_str()) != 0 && errno != ENOENT) return fail(VMIG_EIO, "unlink %s: %s", p.c_str(), errno_str(errno).c_str());
+            std::string base;
+            int rc = parent_of(e.rel, &base);
+            if (rc) return rc;
+            if (unlinkat(pfd, base.c_str(), 0) != 0 && errno != ENOENT) return fail(VMIG_EIO, "unlink %s: %s", e.rel.c_str(), errno_str(errno).c_str());
         }
         return VMIG_OK;
     };
     int rc;
-    if ((rc = rm(m.files)) || (rc = rm(m.symlinks)) || (rc = rm(m.specials))) return rc;
+    if ((rc = rm(m.files)) || (rc = rm(m.symlinks)) || (rc = rm(m.specials))) return finish(rc);
     for (size_t i = m.dirs.size(); i-- > 1;) {
-        const std::string p = join(src_root, m.dirs[i].rel);
-        if (rmdir(p.c_str()) != 0 && errno != ENOENT && errno != ENOTEMPTY)
-            return fail(VMIG_EIO, "rmdir %s: %s", p.c_str(), errno_str(errno).c_str());
+        std::string base;
+        rc = parent_of(m.dirs[i].rel, &base);
+        if (rc) return finish(rc);
+        if (unlinkat(pfd, base.c_str(), AT_REMOVEDIR) != 0 && errno != ENOENT && errno != ENOTEMPTY)
+            return finish(fail(VMIG_EIO, "rmdir %s: %s", m.dirs[i].rel.c_str(), errno_str(errno).c_str()));
     }
-    return VMIG_OK;
+    return finish(VMIG_OK);
 }
 
 }  // namespace vmig

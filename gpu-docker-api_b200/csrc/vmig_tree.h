@@ -43,6 +43,12 @@ struct Manifest {
     uint64_t sockets_skipped = 0;
 };
 
+// Open `rel` (a manifest path) beneath root_fd with `flags`, refusing every symlink on the way and every
+// escape from the root (openat2 RESOLVE_BENEATH|RESOLVE_NO_SYMLINKS; a component-wise O_NOFOLLOW walk on
+// kernels without it).  A path that stopped being plain since the walk fails with VMIG_ESRCCHANGED.
+int open_beneath(int root_fd, const std::string& rel, int flags, int* out_fd);
+int open_beneath_walk(int root_fd, const std::string& rel, int flags, int* out_fd);   // the fallback, exposed for tests/tree_unit.cpp
+
 // Walk src_root.  skip_hidden_topdirs reproduces `mv /root/src/*` (reference utils/copy.go:116).
 int walk_tree(const std::string& src_root, uint32_t block_bytes, bool skip_hidden_topdirs, Manifest* out);
 

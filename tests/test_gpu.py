@@ -7,6 +7,7 @@ import os
 import shutil
 import stat
 import threading
+import time
 from pathlib import Path
 
 import numpy as np
@@ -422,6 +423,53 @@ def test_verify_flag_catches_a_corrupted_destination(vm, orc, shm_tmp, monkeypat
     monkeypatch.delenv("VMIG_CORRUPT_BLOCK")
     vm.migrate_tree(src, dst, None, None, flags=vm.F_VERIFY | vm.F_MOVE_SRC)
     assert os.listdir(src) == [] and sorted(os.listdir(dst)) == ["a.bin", "b.bin"]
+
+
+def test_source_swapped_for_symlink_mid_copy_never_leaks(vm, shm_tmp):
+    """The source layer can belong to a tenant that is still running (first pass of a two-pass hand-off).  While
+    migrations run, a thread keeps swapping src/victim/ for a symlink to a directory OUTSIDE the tree that holds
+    same-named files.  Whatever the interleaving, no byte from outside may reach the destination: a call either
+    copies the real files or fails with VMIG_ESRCCHANGED/VMIG_EIO (the reference's `tar c .` walks by directory
+    descriptor in the same way)."""
+    import threading
+    src, outside = shm_tmp / "src", shm_tmp / "outside"
+    (src / "victim").mkdir(parents=True), (src / "calm").mkdir(), outside.mkdir()
+    real, secret = b"R" * (1 << 20), b"SECRET-OUTSIDE!!" * (1 << 16)
+    for i in range(48):
+        (src / "victim" / f"f{i:02d}").write_bytes(real)
+        (outside / f"f{i:02d}").write_bytes(secret)
+        (src / "calm" / f"g{i:02d}").write_bytes(real)
+    stop = threading.Event()
+
+    def swapper():
+        v, bak = src / "victim", src / "victim.bak"
+        while not stop.is_set():
+            os.rename(v, bak); os.symlink(outside, v)
+            time.sleep(0.0005)
+            os.unlink(v); os.rename(bak, v)
+            time.sleep(0.0005)
+
+    t = threading.Thread(target=swapper); t.start()
+    outcomes = {"ok": 0, "refused": 0}
+    try:
+        for rep in range(12):
+            dst = shm_tmp / f"dst{rep}"
+            dst.mkdir()
+            try:
+                vm.migrate_tree(src, dst, None, None)
+                outcomes["ok"] += 1
+            except vm.VmigError as e:
+                assert e.code in (vm.VMIG_ESRCCHANGED, vm.VMIG_EIO), e
+                outcomes["refused"] += 1
+            for root, _dirs, files in os.walk(dst, followlinks=False):
+                for f in files:
+                    p = Path(root) / f
+                    if not p.is_symlink():
+                        assert b"SECRET" not in p.read_bytes()[:64], f"{p} holds bytes from outside the source tree"
+            shutil.rmtree(dst)
+    finally:
+        stop.set(); t.join()
+    assert outcomes["ok"] + outcomes["refused"] == 12
 
 
 def test_side_stream_limit_option(vm, orc, shm_tmp):

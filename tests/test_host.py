@@ -51,6 +51,20 @@ def test_c_abi_from_plain_c(vm, shm_tmp):
         assert "no CPU fallback" in r.stdout and os.listdir(dst) == []
 
 
+def test_source_side_path_safety_unit(shm_tmp):
+    """csrc/vmig_tree.cpp alone (no GPU, no CUDA): open_beneath refuses symlinks and escapes, the walk does not
+    descend through symlinked directories, remove_source cannot be steered out of the tree."""
+    import subprocess
+    exe = shm_tmp / "tree_unit"
+    csrc = ROOT / "gpu-docker-api_b200" / "csrc"
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", str(csrc), str(ROOT / "tests" / "tree_unit.cpp"),
+                    str(csrc / "vmig_tree.cpp"), "-o", str(exe)], check=True)
+    work = shm_tmp / "tu"
+    work.mkdir()
+    r = subprocess.run([str(exe), str(work)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "tree unit ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_struct_layouts_match_header(vm):
     assert ctypes.sizeof(vm.Opts) == 32
     assert ctypes.sizeof(vm.Stats) == 18 * 8 + 8 + 8
