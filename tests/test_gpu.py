@@ -403,6 +403,32 @@ def test_injected_fault_is_reported_not_swallowed(vm, orc, shm_tmp, monkeypatch)
     assert (dst / "x.bin").read_bytes() == (src / "x.bin").read_bytes()
 
 
+def test_destination_out_of_space_fails_the_call(vm, orc, shm_tmp):
+    """A real write error (ENOSPC on a 48 MiB tmpfs taking a 120 MiB tree) surfaces as VMIG_EIO with the errno
+    text, leaves no descriptor open on the mount (it unmounts), and the engine keeps working."""
+    import subprocess
+    small = shm_tmp / "small"
+    small.mkdir()
+    if subprocess.run(["mount", "-t", "tmpfs", "-o", "size=48m", "tmpfs", str(small)], capture_output=True).returncode != 0:
+        pytest.skip("cannot mount a tmpfs here")
+    try:
+        src = shm_tmp / "src"
+        src.mkdir()
+        for i in range(6):
+            (src / f"f{i}.bin").write_bytes(orc.splitmix_bytes(70 + i, 20 * MiB).tobytes())
+        with pytest.raises(vm.VmigError) as ei:
+            vm.migrate_tree(src, small, None, shm_tmp / "t.vmig", flags=vm.F_MOVE_SRC)
+        assert ei.value.code == vm.VMIG_EIO and "No space left" in str(ei.value)
+        assert not (shm_tmp / "t.vmig").exists() and len(os.listdir(src)) == 6        # a failed move keeps its source
+    finally:
+        r = subprocess.run(["umount", str(small)], capture_output=True, text=True)
+    assert r.returncode == 0, "destination descriptors were left open: " + r.stderr
+    dst = shm_tmp / "dst"
+    dst.mkdir()
+    vm.migrate_tree(src, dst, None, None)
+    assert orc.compare_trees(src, dst) == []
+
+
 def test_verify_flag_catches_a_corrupted_destination(vm, orc, shm_tmp, monkeypatch):
     """VMIG_F_VERIFY re-reads the destination through the GPU; a block that reached the disk wrong
     (test hook flips one bit while writing) fails the call, and a move then keeps its source."""
