@@ -9,6 +9,7 @@
 #include <unistd.h>
 #include <sys/resource.h>
 #include <sys/mman.h>
+#include <sys/syscall.h>
 #include <condition_variable>
 #include <deque>
 #include <thread>
@@ -92,6 +93,17 @@ static int ring_alloc(uint8_t** out, size_t bytes, size_t* mapped)
             if (tail) munmap(a + len, tail);
             madvise(a, len, MADV_HUGEPAGE);
             madvise(a, len, MADV_DONTFORK);        // a forked child (the control plane exec's tools) must not share DMA targets
+            if (env_long("VMIG_RING_MBIND", 0) != 0) {
+                // experiment knob (off by default, untested on the bench box in round 1): give the ring an explicit
+                // memory policy (preferred = the creating thread's node, which is the GPU's) -- VMAs with their own
+                // policy are skipped by the kernel's automatic NUMA-balancing scanner, whose PROT_NONE sweeps and
+                // TLB shootdowns hit every thread of a many-lane process
+                unsigned cpu = 0, node = 0;
+                if (syscall(SYS_getcpu, &cpu, &node, nullptr) == 0 && node < 64) {
+                    unsigned long mask = 1ul << node;
+                    syscall(SYS_mbind, a, len, 1 /* MPOL_PREFERRED */, &mask, 65ul, 0u);
+                }
+            }
             memset(a, 0, len);
             if (cudaHostRegister(a, len, cudaHostRegisterPortable) == cudaSuccess) { *out = a; *mapped = len; return VMIG_OK; }
             cudaGetLastError();
