@@ -37,6 +37,16 @@ func CopyDir(src, dest string) error {
 // under the per-version directory setToMergeMap already creates
 // (internal/services/replicaset.go:681-704): merges/<rs>/<rs>-<v>/blocks.vmig.
 func CopyDirDiff(src, dest, priorTable, outTable string) error {
+	return copyDirDiff(src, dest, priorTable, outTable, 0)
+}
+
+// CopyDirDiffVerified additionally re-reads the destination through the GPU and compares block tables
+// (VMIG_F_VERIFY) before it reports success: for the pass after which the old container is deleted.
+func CopyDirDiffVerified(src, dest, priorTable, outTable string) error {
+	return copyDirDiff(src, dest, priorTable, outTable, C.VMIG_F_VERIFY)
+}
+
+func copyDirDiff(src, dest, priorTable, outTable string, flags C.uint32_t) error {
 	cs, cd := C.CString(src), C.CString(dest)
 	defer C.free(unsafe.Pointer(cs))
 	defer C.free(unsafe.Pointer(cd))
@@ -50,7 +60,9 @@ func CopyDirDiff(src, dest, priorTable, outTable string) error {
 		defer C.free(unsafe.Pointer(co))
 	}
 	var st C.vmig_stats
-	rc := C.vmig_migrate_tree(cs, cd, cp, co, nil, &st)
+	var o C.vmig_opts // zero value = defaults (all GPUs, 4 MiB blocks)
+	o.flags = flags
+	rc := C.vmig_migrate_tree(cs, cd, cp, co, &o, &st)
 	if rc == 0 {
 		log.Infof("vmig: %d bytes, %d/%d blocks skipped, %.2f GiB/s", uint64(st.bytes_total),
 			uint64(st.blocks_skipped), uint64(st.blocks_total),
