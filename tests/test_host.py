@@ -138,6 +138,45 @@ def test_block_table_reader_accepts_good_and_rejects_bad(vm, orc, shm_tmp):
         vm.table_info(shm_tmp / "gap")
 
 
+def test_block_table_reader_survives_corruption(vm, shm_tmp):
+    """A prior table is an input file: 400 random truncations / byte flips / count edits of a valid table are
+    either rejected with VMIG_ETABLE or load as a self-consistent table -- the reader never crashes or over-reads
+    (each mutant is parsed in this process, so a wild read would take the test run down)."""
+    rng = np.random.default_rng(7)
+    entries = [(f"d{i % 7}/f{i:03d}.bin".encode(), int(rng.integers(0, 20 << 20)), 0) for i in range(40)]
+    entries.sort()
+    fixed, fb = [], 0
+    for rel, size, _ in entries:
+        fixed.append((rel, size, fb))
+        fb += (size + (4 << 20) - 1) // (4 << 20)
+    raw = bytearray(_write_table(shm_tmp / "good.vmig", fixed, [int(x) for x in rng.integers(0, 1 << 63, fb)]))
+    assert vm.table_info(shm_tmp / "good.vmig")["n_blocks"] == fb
+    p = shm_tmp / "mut.vmig"
+    rejected = 0
+    for k in range(400):
+        m = bytearray(raw)
+        kind = k % 4
+        if kind == 0:
+            m = m[: int(rng.integers(0, len(m)))]
+        elif kind == 1:
+            for _ in range(int(rng.integers(1, 6))):
+                m[int(rng.integers(0, len(m)))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 2:                                   # header counts / a path length blown up
+            off = int(rng.choice([8, 16, 24, 32]))
+            m[off:off + 4] = int(rng.integers(0, 1 << 32)).to_bytes(4, "little")
+        else:
+            m += bytes(int(rng.integers(1, 64)))
+        p.write_bytes(bytes(m))
+        try:
+            info = vm.table_info(p)
+            h = vm.table_hashes(p)
+            assert len(h) == info["n_blocks"] and info["n_files"] <= 40 + 1
+        except vm.VmigError as e:
+            assert e.code == vm.VMIG_ETABLE, e
+            rejected += 1
+    assert rejected > 200          # most mutants are structurally broken; flips inside hashes/sizes may load
+
+
 def test_manifest_pass_matches_oracle_walk(vm, orc, shm_tmp):
     """The engine's tree walk (ordering, block layout, hard links, specials, the `mv *` quirk) against the
     oracle's independent walk -- no GPU involved (vmig_manifest)."""
