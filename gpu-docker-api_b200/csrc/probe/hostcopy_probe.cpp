@@ -3,7 +3,7 @@
 // buffer, pwrite it to (a) a new tmpfs file, (b) a file whose pages already exist.  Chunk 4 MiB (a libvmig
 // block; falls out of L2) or 256 KiB (cache resident, what tar's pipe does).  Tells whether libvmig's
 // ~20-25 GiB/s end-to-end plateau is the page cache itself or the DMA traffic next to it.
-//   g++ -O2 -o hostcopy_probe hostcopy_probe.cpp -lpthread ; ./hostcopy_probe /dev/shm/vmig_hcp
+//   g++ -O2 -o hostcopy_probe hostcopy_probe.cpp -lpthread ; ./hostcopy_probe /dev/shm/vmig_hcp [MiB per file=512] [split]
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <sys/wait.h>
@@ -26,6 +26,8 @@ int main(int argc, char** argv) {
         char* b = (char*)malloc(4 << 20); memset(b, t + 1, 4 << 20);
         for (size_t o = 0; o < FB; o += 4 << 20) if (pwrite(fd, b, 4 << 20, o) < 0) exit(1);
         close(fd); free(b); });
+    const bool only_split = argc > 3 && std::string(argv[3]) == "split";     // just the processes-x-threads part
+    if (!only_split)
     for (size_t chunk : {(size_t)4 << 20, (size_t)256 << 10})
         for (int T : {4, 8, 16, 24, 32, 48, 64})
             for (int pass = 0; pass < 2; pass++) {      // 0: new destination files, 1: overwrite their pages
@@ -67,6 +69,7 @@ int main(int argc, char** argv) {
         printf("chunk 4096 KiB  %2d processes x %2d threads  new files  %6.2f GiB/s\n", P, T, W * (double)FB / dt / (1 << 30)); fflush(stdout);
     }
     // in-kernel copy (one memcpy per byte instead of two): copy_file_range tmpfs -> tmpfs
+    if (!only_split)
     for (int T : {8, 16, 32, 64}) {
         for (int t = 0; t < TMAX; t++) unlink((dir + "/d" + std::to_string(t)).c_str());
         double t0 = now();
