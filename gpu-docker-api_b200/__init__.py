@@ -35,6 +35,7 @@ VMIG_OK, VMIG_EINVAL, VMIG_ENOGPU, VMIG_ECUDA, VMIG_EIO = 0, -1, -2, -3, -4
 VMIG_ENOMEM, VMIG_ETABLE, VMIG_EFAULT, VMIG_ENOTDIR, VMIG_ESRCCHANGED, VMIG_EVERIFY = -5, -6, -7, -8, -9, -10
 F_MOVE_SRC, F_SKIP_HIDDEN_TOPDIRS, F_MTIME_NS, F_NO_METADATA, F_HASH_ONLY, F_VERIFY = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
 BLOCK_BYTES = 4 << 20
+MOVE_DIR_FLAGS = F_MOVE_SRC | F_VERIFY          # what vmig_move_dir passes (include/vmig.h)
 
 EXPORTS = [
     "vmig_init", "vmig_shutdown", "vmig_device_count", "vmig_strerror", "vmig_last_error", "vmig_version",
@@ -42,20 +43,21 @@ EXPORTS = [
     "vmig_host_free", "vmig_hash_blocks", "vmig_resident_open", "vmig_resident_close", "vmig_resident_fill",
     "vmig_resident_set_len", "vmig_resident_upload", "vmig_resident_download", "vmig_resident_flip",
     "vmig_resident_set_prior", "vmig_resident_pass", "vmig_resident_results", "vmig_table_info_read",
-    "vmig_table_hashes", "vmig_dir_size", "vmig_to_bytes", "vmig_datagen_files", "vmig_manifest",
+    "vmig_table_hashes", "vmig_dir_size", "vmig_to_bytes", "vmig_datagen_files", "vmig_manifest", "vmig_link_probe",
 ]
 
 
 class Opts(C.Structure):
     _fields_ = [("gpu_mask", C.c_uint32), ("block_bytes", C.c_uint32), ("streams_per_gpu", C.c_uint32),
-                ("flags", C.c_uint32), ("io_threads", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("flags", C.c_uint32), ("io_threads", C.c_uint32), ("lanes_per_gpu", C.c_uint32),
+                ("reserved", C.c_uint32 * 2)]
 
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "bytes_total", "bytes_h2d", "bytes_d2h", "bytes_written", "blocks_total", "blocks_skipped", "files", "dirs",
         "symlinks", "hardlinks", "specials", "kernel_launches", "ns_total", "ns_walk", "ns_plan", "ns_data",
-        "ns_meta", "ns_table")] + [("ms_kernel", C.c_double), ("gpus_used", C.c_uint32), ("reserved", C.c_uint32)]
+        "ns_meta", "ns_table")] + [("ms_kernel", C.c_double), ("gpus_used", C.c_uint32), ("lanes_used", C.c_uint32)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
@@ -102,6 +104,7 @@ _sig = {
     "vmig_to_bytes": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64)]),
     "vmig_datagen_files": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32]),
     "vmig_manifest": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(Stats)]),
+    "vmig_link_probe": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_double)]),
 }
 for _n, (_r, _a) in _sig.items():
     _f = getattr(_lib, _n)
@@ -214,9 +217,9 @@ def ToBytes(origin: str) -> int:
 # ------------------------------------------------------------------------------------------------
 # engine entry points
 def migrate_tree(src, dst, prior_table=None, out_table=None, *, gpu_mask: int = 0, flags: int = 0,
-                 block_bytes: int = 0, io_threads: int = 0, streams_per_gpu: int = 0) -> dict:
+                 block_bytes: int = 0, io_threads: int = 0, streams_per_gpu: int = 0, lanes_per_gpu: int = 0) -> dict:
     o = Opts(gpu_mask=gpu_mask, block_bytes=block_bytes, flags=flags, io_threads=io_threads,
-             streams_per_gpu=streams_per_gpu)
+             streams_per_gpu=streams_per_gpu, lanes_per_gpu=lanes_per_gpu)
     st = Stats()
     _check(_lib.vmig_migrate_tree(_b(src), _b(dst), _b(prior_table), _b(out_table), C.byref(o), C.byref(st)),
            f"vmig_migrate_tree({src} -> {dst})")
@@ -328,6 +331,13 @@ class Resident:
         _check(_lib.vmig_resident_results(self.h, hashes.ctypes.data, surv.ctypes.data, C.byref(ns)),
                "vmig_resident_results")
         return hashes, surv[:ns.value].copy()
+
+
+def link_probe(gpu: int = 0, nbytes: int = 4 << 30) -> dict:
+    """Pinned cudaMemcpyAsync sweep: GB/s host->HBM, HBM->host, and both at once (the e2e roofline denominators)."""
+    g = (C.c_double * 4)()
+    _check(_lib.vmig_link_probe(gpu, nbytes, g), "vmig_link_probe")
+    return {"h2d_GBps": g[0], "d2h_GBps": g[1], "duplex_h2d_GBps": g[2], "duplex_d2h_GBps": g[3]}
 
 
 def manifest(src, out_table=None, *, flags: int = 0, block_bytes: int = 0) -> dict:

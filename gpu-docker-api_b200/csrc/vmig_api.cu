@@ -178,7 +178,14 @@ int run_blocks(const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior,
     int rc = ctx_select(o.gpu_mask, &devs);
     if (rc) return rc;
     if (blocks.empty()) { st->gpus_used = 0; return VMIG_OK; }
-    size_t lanes = std::min(devs.size(), blocks.size());
+    // lanes: one per GPU of the mask, times lanes_per_gpu (lane i runs on GPU i % n_gpus); the split below
+    // does not care whether two lanes share a device
+    uint32_t lpg = o.lanes_per_gpu ? o.lanes_per_gpu : (uint32_t)std::max<long>(1, env_long("VMIG_LANES_PER_GPU", 1));
+    if (lpg > 16) lpg = 16;
+    const size_t n_gpus = devs.size();
+    size_t lanes = std::min(n_gpus * lpg, blocks.size());
+    std::vector<DeviceInfo> lane_devs(lanes);
+    for (size_t i = 0; i < lanes; i++) lane_devs[i] = devs[i % n_gpus];
     uint64_t total = 0;
     for (auto& b : blocks) total += std::max<uint32_t>(b.len, 4096);
     std::vector<std::vector<BlockRef>> share(lanes);
@@ -218,11 +225,9 @@ int run_blocks(const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior,
         for (size_t i = 0; i < blocks.size() && i < 256; i++) seen[io->write_key(blocks[i])] = 1;
         io_threads_default(&readers, &writers, o.io_threads, lanes, seen.size() >= 32, has_prior, hash_only);
     }
-    std::vector<Pipe*> pipes(lanes, nullptr);
-    for (size_t i = 0; i < lanes; i++) {
-        rc = ctx_acquire_pipe(devs[i], &pipes[i]);
-        if (rc) { for (size_t j = 0; j < i; j++) ctx_release_pipe(pipes[j]); return rc; }
-    }
+    std::vector<Pipe*> pipes;
+    rc = ctx_acquire_pipes(lane_devs, &pipes);
+    if (rc) return rc;
     std::atomic<int> err{0}; std::string err_msg; std::mutex err_mu;
     std::vector<LaneStats> ls(lanes);
     std::vector<std::thread> th;
@@ -236,7 +241,8 @@ int run_blocks(const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior,
         st->bytes_h2d += l.bytes_h2d; st->bytes_d2h += l.bytes_d2h; st->bytes_written += l.bytes_written;
         st->blocks_skipped += l.blocks_skipped; st->kernel_launches += l.kernel_launches; st->ms_kernel += l.ms_kernel;
     }
-    st->gpus_used = (uint32_t)lanes;
+    st->gpus_used = (uint32_t)std::min(n_gpus, lanes);
+    st->lanes_used = (uint32_t)lanes;          // lanes the block list was sharded over
     if (err.load()) { set_last_error_str(err_msg); return err.load(); }
     return VMIG_OK;
 }
@@ -402,7 +408,16 @@ int migrate_tree_impl(const char* src_dir, const char* dst_dir, const char* prio
     }
     st.ns_table = now_ns() - t0;
 
-    if ((o.flags & VMIG_F_MOVE_SRC) && !hash_only) { rc = remove_source(src, man); if (rc) return rc; }
+    if ((o.flags & VMIG_F_MOVE_SRC) && !hash_only) {
+        // the old volume's data is about to be unlinked: deferred write-back errors (ENOSPC / EIO on delayed
+        // allocation, network filesystems) must surface first.  A no-op on tmpfs; one flush on a disk.
+        int dfd = open(dst.c_str(), O_RDONLY | O_DIRECTORY | O_CLOEXEC);
+        if (dfd < 0) return fail(VMIG_EIO, "open %s: %s", dst.c_str(), errno_str(errno).c_str());
+        const int sr = syncfs(dfd); const int se = errno;
+        close(dfd);
+        if (sr != 0) return fail(VMIG_EIO, "syncfs %s: %s (source left in place)", dst.c_str(), errno_str(se).c_str());
+        rc = remove_source(src, man); if (rc) return rc;
+    }
 
     st.bytes_total = man.bytes_total; st.blocks_total = man.n_blocks;
     st.files = man.files.size(); st.dirs = man.dirs.size();
@@ -447,7 +462,9 @@ int vmig_migrate_tree(const char* src_dir, const char* dst_dir, const char* prio
 int vmig_copy_dir(const char* src_dir, const char* dst_dir) { return migrate_tree_impl(src_dir, dst_dir, nullptr, nullptr, nullptr, nullptr); }
 int vmig_move_dir(const char* src_dir, const char* dst_dir)
 {
-    vmig_opts o; memset(&o, 0, sizeof o); o.flags = VMIG_F_MOVE_SRC;
+    // a move destroys the only other copy: the destination is re-read through the GPU and must hash like the
+    // source (VMIG_F_VERIFY) and is flushed (syncfs) before anything is unlinked
+    vmig_opts o; memset(&o, 0, sizeof o); o.flags = VMIG_F_MOVE_SRC | VMIG_F_VERIFY;
     return migrate_tree_impl(src_dir, dst_dir, nullptr, nullptr, &o, nullptr);
 }
 
@@ -511,6 +528,80 @@ int vmig_hash_blocks(int gpu, const void* host_buf, const uint64_t* offs, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// host<->HBM link probe
+#define CU_API(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cudaGetLastError(); return fail(e__ == cudaErrorMemoryAllocation ? VMIG_ENOMEM : VMIG_ECUDA, "%s: %s", #call, cudaGetErrorString(e__)); } } while (0)
+
+static int link_probe_here(int gpu, uint64_t bytes, double* gbs)
+{
+    const size_t piece = 32u << 20, ring = 8;           // 8 x 32 MiB per direction: larger than any host cache
+    CU_API(cudaSetDevice(gpu));
+    uint8_t *h_a = nullptr, *h_b = nullptr, *d_a = nullptr, *d_b = nullptr;
+    cudaStream_t s0 = nullptr, s1 = nullptr; cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    auto cleanup = [&] {
+        if (h_a) cudaFreeHost(h_a); if (h_b) cudaFreeHost(h_b); if (d_a) cudaFree(d_a); if (d_b) cudaFree(d_b);
+        if (s0) cudaStreamDestroy(s0); if (s1) cudaStreamDestroy(s1);
+        for (auto& x : e) if (x) cudaEventDestroy(x);
+    };
+    auto run = [&]() -> int {
+        CU_API(cudaHostAlloc((void**)&h_a, piece * ring, cudaHostAllocPortable)); memset(h_a, 1, piece * ring);
+        CU_API(cudaHostAlloc((void**)&h_b, piece * ring, cudaHostAllocPortable)); memset(h_b, 2, piece * ring);
+        CU_API(cudaMalloc((void**)&d_a, piece * ring)); CU_API(cudaMalloc((void**)&d_b, piece * ring));
+        CU_API(cudaMemset(d_b, 3, piece * ring));
+        CU_API(cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking)); CU_API(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+        for (auto& x : e) CU_API(cudaEventCreate(&x));
+        const uint64_t n = std::max<uint64_t>(1, bytes / piece);
+        auto pass = [&](bool up, bool down, double* up_gbs, double* down_gbs) -> int {
+            for (int rep = 0; rep < 2; rep++) {          // rep 0 warms up
+                if (up) CU_API(cudaEventRecord(e[0], s0));
+                if (down) CU_API(cudaEventRecord(e[2], s1));
+                for (uint64_t i = 0; i < n; i++) {
+                    const size_t o = (size_t)(i % ring) * piece;
+                    if (up) CU_API(cudaMemcpyAsync(d_a + o, h_a + o, piece, cudaMemcpyHostToDevice, s0));
+                    if (down) CU_API(cudaMemcpyAsync(h_b + o, d_b + o, piece, cudaMemcpyDeviceToHost, s1));
+                }
+                if (up) CU_API(cudaEventRecord(e[1], s0));
+                if (down) CU_API(cudaEventRecord(e[3], s1));
+                CU_API(cudaStreamSynchronize(s0)); CU_API(cudaStreamSynchronize(s1));
+            }
+            float ms = 0;
+            if (up) { CU_API(cudaEventElapsedTime(&ms, e[0], e[1])); *up_gbs = (double)(n * piece) / (ms * 1e-3) / 1e9; }
+            if (down) { CU_API(cudaEventElapsedTime(&ms, e[2], e[3])); *down_gbs = (double)(n * piece) / (ms * 1e-3) / 1e9; }
+            return VMIG_OK;
+        };
+        double dummy = 0;
+        int rc = pass(true, false, &gbs[0], &dummy); if (rc) return rc;
+        rc = pass(false, true, &dummy, &gbs[1]); if (rc) return rc;
+        return pass(true, true, &gbs[2], &gbs[3]);
+    };
+    const int rc = run();
+    const std::string keep = rc ? last_error_cstr() : "";
+    cleanup();
+    if (rc) set_last_error_str(keep);
+    return rc;
+}
+
+int vmig_link_probe(int gpu, uint64_t bytes, double gbs[4])
+{
+    if (!gbs || gpu < 0 || gpu > 31) return fail(VMIG_EINVAL, "bad link-probe arguments");
+    std::vector<DeviceInfo> devs; int rc = ctx_select(1u << gpu, &devs); if (rc) return rc;
+    gbs[0] = gbs[1] = gbs[2] = gbs[3] = 0;
+    // allocate and first-touch the pinned buffers on the GPU's NUMA node, like the staging rings
+    std::string msg;
+    std::thread t([&] {
+        if (!devs[0].cpus.empty()) {
+            cpu_set_t set; CPU_ZERO(&set);
+            for (int c : devs[0].cpus) if (c < CPU_SETSIZE) CPU_SET(c, &set);
+            sched_setaffinity(0, sizeof set, &set);
+        }
+        rc = link_probe_here(gpu, bytes ? bytes : (4ull << 30), gbs);
+        if (rc) msg = last_error_cstr();
+    });
+    t.join();
+    if (rc) set_last_error_str(msg);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // HBM-resident batch
 struct vmig_resident {
     int dev; int sm_count; uint64_t n; uint32_t block_bytes;
@@ -519,7 +610,6 @@ struct vmig_resident {
     bool has_prior; cudaStream_t stream; cudaEvent_t e0, e1, e2, e3;
 };
 
-#define CU_API(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cudaGetLastError(); return fail(e__ == cudaErrorMemoryAllocation ? VMIG_ENOMEM : VMIG_ECUDA, "%s: %s", #call, cudaGetErrorString(e__)); } } while (0)
 
 void vmig_resident_close(vmig_resident* r);
 

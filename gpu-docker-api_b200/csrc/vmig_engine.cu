@@ -294,32 +294,85 @@ int ctx_select(uint32_t mask, std::vector<DeviceInfo>* out)
 
 static std::atomic<long> g_active_lanes{0};     // pipes checked out by calls in flight in this process
 
+// Check out one Pipe per entry of lane_devs (a device may appear several times: lanes_per_gpu).  The
+// whole set is reserved in ONE step under the lock -- a call that needs k pipes of one GPU never holds
+// some of them while waiting for the rest, so two such calls cannot deadlock each other.  The per-GPU
+// cap (VMIG_PIPES_PER_GPU) grows to what a single call asks for.
+int ctx_acquire_pipes(const std::vector<DeviceInfo>& lane_devs, std::vector<Pipe*>* out)
+{
+    out->assign(lane_devs.size(), nullptr);
+    std::vector<int> need_dev; std::vector<uint32_t> need_cnt;
+    for (auto& d : lane_devs) {
+        size_t k = 0; while (k < need_dev.size() && need_dev[k] != d.dev) k++;
+        if (k == need_dev.size()) { need_dev.push_back(d.dev); need_cnt.push_back(0); }
+        need_cnt[k]++;
+    }
+    std::vector<uint32_t> to_create(need_dev.size(), 0);
+    {
+        std::unique_lock<std::mutex> lk(g_mu);
+        for (;;) {
+            bool ok = true;
+            for (size_t k = 0; k < need_dev.size() && ok; k++) {
+                DevPool* dp = nullptr;
+                for (auto& x : g_devs) if (x.info.dev == need_dev[k]) dp = &x;
+                if (!dp) return fail(VMIG_ENOGPU, "device %d not initialised", need_dev[k]);
+                const uint32_t cap = std::max(g_pipes_per_gpu, need_cnt[k]);
+                const uint32_t room = dp->n_pipes < cap ? cap - dp->n_pipes : 0;
+                if (dp->free_pipes.size() + room < need_cnt[k]) ok = false;
+            }
+            if (ok) break;
+            g_cv.wait(lk);
+        }
+        for (size_t k = 0; k < need_dev.size(); k++) {
+            DevPool* dp = nullptr;
+            for (auto& x : g_devs) if (x.info.dev == need_dev[k]) dp = &x;
+            uint32_t left = need_cnt[k];
+            for (size_t i = 0; i < lane_devs.size() && left; i++) {
+                if (lane_devs[i].dev != need_dev[k] || (*out)[i]) continue;
+                if (dp->free_pipes.empty()) break;
+                (*out)[i] = dp->free_pipes.back(); dp->free_pipes.pop_back(); left--;
+            }
+            to_create[k] = left; dp->n_pipes += left;        // reserved; created outside the lock
+        }
+    }
+    // new pipes of different lanes are created in parallel (page-locking 1 GiB of rings takes ~0.35 s each)
+    int rc = VMIG_OK; std::string msg; std::mutex rmu;
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < lane_devs.size(); i++) {
+        if ((*out)[i]) continue;
+        th.emplace_back([&, i] {
+            Pipe* p = new Pipe();
+            int r = p->create(lane_devs[i]);
+            if (r) {
+                std::lock_guard<std::mutex> lk(rmu);
+                if (!rc) { rc = r; msg = last_error_cstr(); }
+                p->destroy(); delete p; return;
+            }
+            (*out)[i] = p;
+        });
+    }
+    for (auto& t : th) t.join();
+    if (rc) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (size_t i = 0; i < lane_devs.size(); i++) {
+            DevPool* dp = nullptr;
+            for (auto& x : g_devs) if (x.info.dev == lane_devs[i].dev) dp = &x;
+            if (!dp) continue;
+            if ((*out)[i]) { dp->free_pipes.push_back((*out)[i]); (*out)[i] = nullptr; }
+            else dp->n_pipes--;
+        }
+        g_cv.notify_all(); set_last_error_str(msg);
+        return rc;
+    }
+    g_active_lanes += (long)lane_devs.size();
+    return VMIG_OK;
+}
 int ctx_acquire_pipe(const DeviceInfo& d, Pipe** out)
 {
-    std::unique_lock<std::mutex> lk(g_mu);
-    for (;;) {
-        DevPool* dp = nullptr;
-        for (auto& x : g_devs) if (x.info.dev == d.dev) dp = &x;
-        if (!dp) return fail(VMIG_ENOGPU, "device %d not initialised", d.dev);
-        if (!dp->free_pipes.empty()) { *out = dp->free_pipes.back(); dp->free_pipes.pop_back(); g_active_lanes++; return VMIG_OK; }
-        if (dp->n_pipes < g_pipes_per_gpu) {
-            dp->n_pipes++;
-            lk.unlock();
-            Pipe* p = new Pipe();
-            int rc = p->create(d);
-            if (rc) {
-                std::string keep = last_error_cstr();
-                p->destroy(); delete p; lk.lock();
-                for (auto& x : g_devs) if (x.info.dev == d.dev) x.n_pipes--;
-                g_cv.notify_all(); set_last_error_str(keep);
-                return rc;
-            }
-            *out = p;
-            g_active_lanes++;
-            return VMIG_OK;
-        }
-        g_cv.wait(lk);
-    }
+    std::vector<Pipe*> v; std::vector<DeviceInfo> one{d};
+    int rc = ctx_acquire_pipes(one, &v);
+    if (!rc) *out = v[0];
+    return rc;
 }
 void ctx_release_pipe(Pipe* p)
 {

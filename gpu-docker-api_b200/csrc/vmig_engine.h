@@ -65,6 +65,8 @@ int  ctx_device_count();
 // devices selected by `mask` (0 = all initialised); error if none
 int  ctx_select(uint32_t mask, std::vector<DeviceInfo>* out);
 int  ctx_acquire_pipe(const DeviceInfo& d, Pipe** out);
+// one Pipe per lane, all reserved atomically (a device may repeat: lanes_per_gpu)
+int  ctx_acquire_pipes(const std::vector<DeviceInfo>& lane_devs, std::vector<Pipe*>* out);
 void ctx_release_pipe(Pipe* p);
 uint32_t pipe_slot_bytes();
 int  io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested, size_t lanes, bool many_files,

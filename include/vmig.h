@@ -67,8 +67,10 @@ const char* vmig_last_error(void);            /* thread-local detail of the last
 const char* vmig_version(void);
 
 /* ---- options / statistics ------------------------------------------------------------------ */
-#define VMIG_F_MOVE_SRC          0x01u  /* unlink source entries after a verified copy: the `mv` of
-                                           moveVolumeData (reference utils/copy.go:116)            */
+#define VMIG_F_MOVE_SRC          0x01u  /* unlink source entries after the copy succeeded and the destination
+                                           was flushed (syncfs): the `mv` of moveVolumeData (reference
+                                           utils/copy.go:116).  Combine with VMIG_F_VERIFY (vmig_move_dir
+                                           does) to also re-hash the destination before unlinking           */
 #define VMIG_F_SKIP_HIDDEN_TOPDIRS 0x02u /* reproduce `mv /root/src/ *`: top-level hidden DIRECTORIES
                                            are left behind (reference utils/copy.go:116)           */
 #define VMIG_F_MTIME_NS          0x04u  /* keep nanosecond mtimes (mv does; GNU tar's default archive
@@ -85,7 +87,12 @@ typedef struct vmig_opts {
     uint32_t streams_per_gpu;  /* side streams = staging slots in flight per GPU; 0 -> all (16)   */
     uint32_t flags;            /* VMIG_F_*                                                       */
     uint32_t io_threads;       /* 0 -> default: host reader+writer threads per GPU               */
-    uint32_t reserved[3];
+    uint32_t lanes_per_gpu;    /* 0/1 -> one lane (staging-ring set + thread pipeline) per GPU of the
+                                  mask; k -> k lanes per GPU, the block list is sharded over
+                                  n_gpus*k lanes exactly as it is over n_gpus*k GPUs (more host
+                                  copy parallelism per link; also how the multi-GPU split is
+                                  exercised on a 1-GPU box).  Env VMIG_LANES_PER_GPU overrides 0. */
+    uint32_t reserved[2];
 } vmig_opts;
 
 typedef struct vmig_stats {
@@ -100,7 +107,7 @@ typedef struct vmig_stats {
     uint64_t ns_total, ns_walk, ns_plan, ns_data, ns_meta, ns_table;
     double   ms_kernel;        /* sum of CUDA-event time of the hash kernels                     */
     uint32_t gpus_used;
-    uint32_t reserved;
+    uint32_t lanes_used;       /* lanes the block list was sharded over (gpus_used * lanes_per_gpu) */
 } vmig_stats;
 
 /* ---- the hot path -------------------------------------------------------------------------- */
@@ -123,8 +130,11 @@ int vmig_migrate_tree(const char* src_dir, const char* dst_dir,
 /* utils.CopyDir(src, dest) (reference utils/copy.go:21-27) == vmig_migrate_tree with defaults. */
 int vmig_copy_dir(const char* src_dir, const char* dst_dir);
 
-/* moveVolumeData(src, dest) on resolved host paths (reference utils/copy.go:74-128): copy then
- * unlink the source entries, nanosecond mtimes, synchronously and with the exit status checked. */
+/* moveVolumeData(src, dest) on resolved host paths (reference utils/copy.go:74-128): copy, re-read the
+ * destination through the GPU and require it to hash like the source (VMIG_F_VERIFY), syncfs the destination,
+ * and only then unlink the source entries; nanosecond mtimes; synchronous, exit status checked.
+ * Divergence from `mv`: sockets are skipped and stay in the source (tar skips them too; a listening socket's
+ * inode means nothing in another volume). */
 int vmig_move_dir(const char* src_dir, const char* dst_dir);
 
 /* Host buffer -> host buffer through the same pipeline (H2D, hash, diff, D2H of survivors).
@@ -165,6 +175,13 @@ int  vmig_resident_set_prior(vmig_resident* r, const uint64_t* hashes, const uin
 int  vmig_resident_pass(vmig_resident* r, uint32_t iters, double* ms_hash_last, double* ms_total);
 int  vmig_resident_results(vmig_resident* r, uint64_t* hashes /*n_blocks, nullable*/,
                            uint32_t* survivors /*n_blocks cap, nullable*/, uint64_t* n_survivors);
+
+/* ---- host<->HBM link probe (the e2e roofline denominator) ----------------------------------
+ * Pinned-memory cudaMemcpyAsync sweep on GPU `gpu`: `bytes` per direction in 32 MiB pieces out of a NUMA-local
+ * page-locked buffer, timed with CUDA events.  gbs[0] = H2D alone, gbs[1] = D2H alone, gbs[2] / gbs[3] = H2D / D2H
+ * while both directions run at once (two streams) -- the state the copy-back path of a migration is in.
+ * GB/s = 1e9 bytes per second. */
+int vmig_link_probe(int gpu, uint64_t bytes, double gbs[4]);
 
 /* ---- block table + host-side helpers (no GPU needed) ---------------------------------------- */
 /* Block-table file, little-endian:

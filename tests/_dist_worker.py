@@ -7,12 +7,15 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import bench  # noqa: E402
 
-rank, world, local, barrier, allmax = bench.dist_setup(int(os.environ["WORLD_SIZE"]))
+rank, world, local, barrier, allmax = bench.dist_setup()
 barrier()
 slowest = allmax(1.0 + rank)              # max over ranks, as the timing rules require
 barrier()
-out = {"rank": rank, "world": world, "local": local, "max": slowest, "gpu_mask": 1 << local,
-       "dir": str(bench.shm_base() / f"vmig_bench_r{rank}")}
+plan = bench.rank_plan("2A", local, world, world)
+solo = {c: bench.rank_plan(c, local, world, world) for c in ("1", "2B", "3", "4", "5")}
+out = {"rank": rank, "world": world, "local": local, "max": slowest, "gpu_mask": plan["own_mask"],
+       "dir": str(bench.shm_base() / plan["tree"]), "seed": plan["seed"], "active_2A": plan["active"],
+       "active_solo": {c: p["active"] for c, p in solo.items()}, "all_mask": solo["3"]["all_mask"]}
 Path(os.environ["VMIG_DIST_OUT"], f"r{rank}.json").write_text(json.dumps(out))
 import torch.distributed as dist  # noqa: E402
 dist.barrier()

@@ -27,7 +27,11 @@ def test_two_rank_barrier_and_max(tmp_path):
     assert [o["rank"] for o in outs] == [0, 1] and all(o["world"] == 2 for o in outs)
     assert all(o["max"] == 2.0 for o in outs)                    # both ranks see the slowest rank's time
     assert outs[0]["gpu_mask"] == 1 and outs[1]["gpu_mask"] == 2  # one GPU per rank
-    assert outs[0]["dir"] != outs[1]["dir"]                      # one tree per rank (weak scaling)
+    assert outs[0]["dir"] != outs[1]["dir"] and outs[0]["seed"] != outs[1]["seed"]   # one tree per rank (weak scaling)
+    assert all(o["active_2A"] for o in outs)
+    # single-call configs (sharded call, caller threads): rank 0 drives every GPU of the box from ONE process
+    assert all(outs[0]["active_solo"].values()) and not any(outs[1]["active_solo"].values())
+    assert outs[0]["all_mask"] == 0b11
 
 
 def test_reference_arm_skips_on_nonzero_rank():

@@ -550,18 +550,42 @@ def test_migrate_buffer_roundtrip_and_diff(vm, orc, pinned):
         a.free(), b.free()
 
 
-def test_multi_gpu_sharding_same_result(vm, orc, shm_tmp):
-    if vm.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
-    src, d1, d2 = shm_tmp / "src", shm_tmp / "d1", shm_tmp / "d2"
-    src.mkdir(), d1.mkdir(), d2.mkdir()
-    for i in range(6):
-        (src / f"f{i}.bin").write_bytes(orc.splitmix_bytes(60 + i, 11 * MiB + i).tobytes())
-    s1 = vm.migrate_tree(src, d1, None, shm_tmp / "t1", gpu_mask=0b01)
-    s2 = vm.migrate_tree(src, d2, None, shm_tmp / "t2", gpu_mask=0b11)
-    assert s1["gpus_used"] == 1 and s2["gpus_used"] == 2
-    assert (shm_tmp / "t1").read_bytes() == (shm_tmp / "t2").read_bytes()
-    assert orc.compare_trees(d1, d2, mtime_ns=True) == []
+@pytest.mark.parametrize("lanes", [2, 3, 8])
+def test_sharded_block_list_matches_oracle(vm, orc, shm_tmp, lanes):
+    """North-star split: ONE call whose block list is sharded over several lanes.  On a 1-GPU box
+    the lanes share the device (vmig_opts.lanes_per_gpu), on an N-GPU box they spread over the GPUs first -- the
+    split, the shared hash array and the cross-lane per-file counters are the same code either way.  Tree and
+    table are compared with the ORACLE (the literal tar pipe, the C XXH64), not with a 1-lane run."""
+    ndev = vm.device_count()
+    gpus = min(ndev, lanes)
+    src, dst, ref = shm_tmp / "src", shm_tmp / "dst", shm_tmp / "ref"
+    (src / "d").mkdir(parents=True), dst.mkdir(), ref.mkdir()
+    sizes = [11 * MiB + 1, 4 * MiB, 4 * MiB - 1, 1, 37 * MiB + 5, 0, 9 * MiB, 123457, 8 * MiB, 5 * MiB + 4095,
+             2 * MiB, 6 * MiB + 31, 3 * MiB + 33, 17, 4 * MiB + 1, 12 * MiB, 70001, 21 * MiB + 7]
+    for i, n in enumerate(sizes):
+        (src / ("d" if i % 3 == 0 else ".") / f"f{i:02d}.bin").write_bytes(orc.splitmix_bytes(600 + i, n).tobytes())
+    os.link(src / "f04.bin", src / "d" / "hard04")
+    os.symlink("f01.bin", src / "lnk")
+    st = vm.migrate_tree(src, dst, None, shm_tmp / "t.vmig", gpu_mask=(1 << gpus) - 1, lanes_per_gpu=-(-lanes // gpus))
+    assert st["gpus_used"] == gpus and st["lanes_used"] >= lanes
+    orc.ref_copy(src, ref)
+    assert orc.compare_trees(ref, dst) == []
+    _, want = orc.block_table_of_tree(src)
+    assert (vm.table_hashes(shm_tmp / "t.vmig") == want).all()
+    # one huge file and fewer files than lanes: the contiguous byte-range split (lanes share a destination file)
+    one, d2 = shm_tmp / "one", shm_tmp / "d2"
+    one.mkdir(), d2.mkdir()
+    (one / "big.bin").write_bytes(orc.splitmix_bytes(77, 61 * MiB + 13).tobytes())
+    st = vm.migrate_tree(one, d2, None, shm_tmp / "t2.vmig", gpu_mask=(1 << gpus) - 1, lanes_per_gpu=-(-lanes // gpus))
+    assert st["lanes_used"] >= lanes
+    assert (d2 / "big.bin").read_bytes() == (one / "big.bin").read_bytes()
+    assert (vm.table_hashes(shm_tmp / "t2.vmig") == orc.hash_file(one / "big.bin")).all()
+    # diff pass against the table just written: only the two mutated blocks move, on whichever lanes own them
+    _mutate(one / "big.bin", 3), _mutate(one / "big.bin", 14)
+    st = vm.migrate_tree(one, d2, shm_tmp / "t2.vmig", shm_tmp / "t3.vmig", gpu_mask=(1 << gpus) - 1,
+                         lanes_per_gpu=-(-lanes // gpus))
+    assert st["blocks_total"] - st["blocks_skipped"] == 2
+    assert (d2 / "big.bin").read_bytes() == (one / "big.bin").read_bytes()
 
 
 def test_full_size_resident_pass_properties(vm, orc):
