@@ -31,6 +31,7 @@ public:
         std::atomic<uint32_t> reads_left{0}, blocks_left{0};
         bool inplace = false;            // diff path: destination file is the prior version, patched in place
         uint64_t dst_old_size = 0;
+        uint64_t id_ino = 0; int64_t id_ctime_ns = 0;   // identity of the file the table will speak for (vmig_table.h)
     };
     std::string src_root, dst_root;
     int src_root_fd = -1;                // source files are opened beneath this descriptor, never by absolute path
@@ -57,6 +58,7 @@ public:
                     close(fd);
                     return fail(VMIG_ESRCCHANGED, "%s is not a regular file any more", m->files[f].rel.c_str());
                 }
+                if (hash_only && st.st_nlink == 1) { s.id_ino = (uint64_t)st.st_ino; s.id_ctime_ns = (int64_t)st.st_ctim.tv_sec * 1000000000ll + st.st_ctim.tv_nsec; }
                 s.sfd.store(fd, std::memory_order_release);
             }
         }
@@ -131,6 +133,8 @@ public:
             close(fd); return fail(VMIG_EIO, "ftruncate %s: %s", p.c_str(), errno_str(errno).c_str());
         }
         rc = apply_file_meta(fd, p, e, pol);
+        struct stat ids;                             // nothing touches the file after this point: its ctime is final
+        if (!rc && fstat(fd, &ids) == 0) { s.id_ino = (uint64_t)ids.st_ino; s.id_ctime_ns = (int64_t)ids.st_ctim.tv_sec * 1000000000ll + ids.st_ctim.tv_nsec; }
         if (close(fd) != 0 && !rc) rc = fail(VMIG_EIO, "close %s: %s", p.c_str(), errno_str(errno).c_str());
         s.dfd.store(-1);
         return rc;
@@ -331,9 +335,16 @@ int migrate_tree_impl(const char* src_dir, const char* dst_dir, const char* prio
         if (has_prior) {
             auto it = prior.index.find(e.rel);
             struct stat ds;
-            if (it != prior.index.end() && lstat(pjoin(dst, e.rel).c_str(), &ds) == 0 && S_ISREG(ds.st_mode) &&
-                ds.st_nlink == 1 && (uint64_t)ds.st_size == prior.files[it->second].size) {
-                s.inplace = true; s.dst_old_size = (uint64_t)ds.st_size;
+            // patch in place only a destination file that still IS the one the table was written for: same
+            // inode, same ctime (any write, truncate, chmod or replacement since then moved it), same size
+            if (it != prior.index.end() && lstat(pjoin(dst, e.rel).c_str(), &ds) == 0 && S_ISREG(ds.st_mode) && ds.st_nlink == 1) {
+                const TableFile& pf = prior.files[it->second];
+                const int64_t ct = (int64_t)ds.st_ctim.tv_sec * 1000000000ll + ds.st_ctim.tv_nsec;
+                if (pf.ino != 0 && (uint64_t)ds.st_ino == pf.ino && ct == pf.ctime_ns && (uint64_t)ds.st_size == pf.size) {
+                    s.inplace = true; s.dst_old_size = (uint64_t)ds.st_size;
+                } else if (pf.ino != 0) {
+                    st.files_untrusted++;
+                }
             }
         }
         group.push_back(f);
@@ -342,6 +353,10 @@ int migrate_tree_impl(const char* src_dir, const char* dst_dir, const char* prio
     flush_group();
     st.ns_plan = now_ns() - t0;
 
+    // VMIG_F_PRUNE runs first: what it removes is by definition not in the source, a directory sitting where the source
+    // now has a file (or the reverse) is out of the way before anything is created, and the directory mtimes restored
+    // at the end are not disturbed by unlinks
+    if ((o.flags & VMIG_F_PRUNE) && !hash_only) { rc = prune_extras(dst, man, false, &st.pruned); if (rc) return rc; }
     if (!hash_only) { rc = make_dirs(dst, man); if (rc) return rc; }
 
     t0 = now_ns();
@@ -364,7 +379,13 @@ int migrate_tree_impl(const char* src_dir, const char* dst_dir, const char* prio
             if (was_dir) return fail(VMIG_EIO, "%s: a directory is in the way of a regular file", p.c_str());
             int fd = open(p.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_CLOEXEC | O_NOFOLLOW, 0600);
             if (fd < 0) return fail(VMIG_EIO, "create %s: %s", p.c_str(), errno_str(errno).c_str());
-            rc = apply_file_meta(fd, p, e, io.pol); close(fd);
+            rc = apply_file_meta(fd, p, e, io.pol);
+            struct stat ids;
+            if (!rc && fstat(fd, &ids) == 0) {
+                FileIO::FS& s = io.fs[&e - &man.files[0]];
+                s.id_ino = (uint64_t)ids.st_ino; s.id_ctime_ns = (int64_t)ids.st_ctim.tv_sec * 1000000000ll + ids.st_ctim.tv_nsec;
+            }
+            close(fd);
             if (rc) return rc;
         }
         rc = replay_metadata(dst, man, io.pol, &st.symlinks, &st.hardlinks, &st.specials);
@@ -395,13 +416,22 @@ int migrate_tree_impl(const char* src_dir, const char* dst_dir, const char* prio
                 return fail(VMIG_EVERIFY, "verify: %s block %llu hashes %016llx in the destination, %016llx in the source",
                             man.files[b.file].rel.c_str(), (unsigned long long)(b.file_off / o.block_bytes),
                             (unsigned long long)vh[b.table_idx], (unsigned long long)hashes[b.table_idx]);
+        if (o.flags & VMIG_F_PRUNE) {               // the destination's entry set must now equal the source's
+            uint64_t extras = 0;
+            rc = prune_extras(dst, man, true, &extras); if (rc) return rc;
+            if (extras) return fail(VMIG_EVERIFY, "verify: %llu destination entries are not in the source after pruning", (unsigned long long)extras);
+        }
     }
 
     t0 = now_ns();
     if (out_path && *out_path) {
         BlockTable t; t.block_bytes = o.block_bytes; t.algo = 1;
         t.files.reserve(man.files.size());
-        for (auto& e : man.files) t.files.push_back({e.rel, e.size, e.first_block});
+        for (uint32_t f = 0; f < man.files.size(); f++) {
+            const Entry& e = man.files[f];
+            const bool own = e.hardlink_of < 0 && (e.n_blocks || !hash_only);         // hard-linked paths are never patched in place
+            t.files.push_back({e.rel, e.size, e.first_block, own ? io.fs[f].id_ino : 0, own ? io.fs[f].id_ctime_ns : 0});
+        }
         t.hashes = hashes;
         rc = table_store(out_path, t);
         if (rc) return rc;

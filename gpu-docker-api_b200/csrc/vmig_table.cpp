@@ -9,7 +9,8 @@
 
 namespace vmig {
 
-static const char kMagic[8] = {'V', 'M', 'I', 'G', 'B', 'T', '0', '1'};
+static const char kMagic1[8] = {'V', 'M', 'I', 'G', 'B', 'T', '0', '1'};   // no file identity
+static const char kMagic[8]  = {'V', 'M', 'I', 'G', 'B', 'T', '0', '2'};   // + u64 ino, i64 ctime_ns per file
 
 int table_load(const std::string& path, BlockTable* t)
 {
@@ -26,7 +27,8 @@ int table_load(const std::string& path, BlockTable* t)
         got += (size_t)r;
     }
     close(fd);
-    if (raw.size() < 32 || memcmp(raw.data(), kMagic, 8) != 0) return fail(VMIG_ETABLE, "%s: bad magic", path.c_str());
+    if (raw.size() < 32 || (memcmp(raw.data(), kMagic, 8) != 0 && memcmp(raw.data(), kMagic1, 8) != 0)) return fail(VMIG_ETABLE, "%s: bad magic", path.c_str());
+    const size_t rec = memcmp(raw.data(), kMagic, 8) == 0 ? 32 : 16;        // fixed bytes per file after the path
     uint64_t n_files, n_blocks;
     memcpy(&t->block_bytes, &raw[8], 4); memcpy(&t->algo, &raw[12], 4);
     memcpy(&n_files, &raw[16], 8); memcpy(&n_blocks, &raw[24], 8);
@@ -38,9 +40,11 @@ int table_load(const std::string& path, BlockTable* t)
     for (uint64_t i = 0; i < n_files; i++) {
         if (off + 4 > raw.size()) return fail(VMIG_ETABLE, "%s: truncated manifest", path.c_str());
         uint32_t plen; memcpy(&plen, &raw[off], 4); off += 4;
-        if (off + plen + 16 > raw.size()) return fail(VMIG_ETABLE, "%s: truncated manifest", path.c_str());
+        if (off + plen + rec > raw.size()) return fail(VMIG_ETABLE, "%s: truncated manifest", path.c_str());
         TableFile f; f.rel.assign(&raw[off], plen); off += plen;
-        memcpy(&f.size, &raw[off], 8); memcpy(&f.first_block, &raw[off + 8], 8); off += 16;
+        memcpy(&f.size, &raw[off], 8); memcpy(&f.first_block, &raw[off + 8], 8);
+        if (rec == 32) { memcpy(&f.ino, &raw[off + 16], 8); memcpy(&f.ctime_ns, &raw[off + 24], 8); }
+        off += rec;
         if (f.first_block != expect_first) return fail(VMIG_ETABLE, "%s: inconsistent first_block for %s", path.c_str(), f.rel.c_str());
         if (!t->files.empty() && !(t->files.back().rel < f.rel)) return fail(VMIG_ETABLE, "%s: manifest not sorted", path.c_str());
         expect_first += t->blocks_of(f);
@@ -58,7 +62,7 @@ int table_store(const std::string& path, const BlockTable& t)
 {
     std::string raw;
     size_t need = 32 + 8 * t.hashes.size();
-    for (auto& f : t.files) need += 4 + f.rel.size() + 16;
+    for (auto& f : t.files) need += 4 + f.rel.size() + 32;
     raw.reserve(need);
     raw.append(kMagic, 8);
     uint64_t n_files = t.files.size(), n_blocks = t.hashes.size();
@@ -68,6 +72,7 @@ int table_store(const std::string& path, const BlockTable& t)
         uint32_t plen = (uint32_t)f.rel.size();
         raw.append((const char*)&plen, 4); raw.append(f.rel);
         raw.append((const char*)&f.size, 8); raw.append((const char*)&f.first_block, 8);
+        raw.append((const char*)&f.ino, 8); raw.append((const char*)&f.ctime_ns, 8);
     }
     if (n_blocks) raw.append((const char*)t.hashes.data(), 8 * (size_t)n_blocks);
 

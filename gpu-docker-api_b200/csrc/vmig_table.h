@@ -11,7 +11,11 @@
 
 namespace vmig {
 
-struct TableFile { std::string rel; uint64_t size; uint64_t first_block; };
+// ino / ctime_ns identify the on-disk file the hashes were taken FOR: the destination file the migration that
+// wrote the table left behind (the source file for a VMIG_F_HASH_ONLY table).  0/0 = unknown (format 01, hard-linked
+// paths).  The in-place diff path trusts a prior table for a destination file only while both still match
+// (ctime cannot be set from user space: any out-of-band write, truncate, chmod or rename-over bumps it).
+struct TableFile { std::string rel; uint64_t size; uint64_t first_block; uint64_t ino = 0; int64_t ctime_ns = 0; };
 
 struct BlockTable {
     uint32_t block_bytes = 0;

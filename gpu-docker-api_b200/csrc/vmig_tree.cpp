@@ -1,5 +1,7 @@
 // vmig_tree.cpp -- source-tree walk and destination metadata replay (see vmig_tree.h).
 #include "vmig_tree.h"
+#include <unordered_set>
+#include <dirent.h>
 #include "vmig_common.h"
 
 #include <dirent.h>
@@ -349,6 +351,74 @@ int remove_source(const std::string& src_root, const Manifest& m)
             return finish(fail(VMIG_EIO, "rmdir %s: %s", m.dirs[i].rel.c_str(), errno_str(errno).c_str()));
     }
     return finish(VMIG_OK);
+}
+
+// ---------------------------------------------------------------------------------------------
+// VMIG_F_PRUNE: make the destination hold nothing the source does not (the final pass of a hand-off: a file the
+// tenant deleted or renamed between the live pass and the paused pass must not reappear in the new container).
+static int rm_tree_at(int dfd, const char* name, uint64_t* n)
+{
+    int fd = openat(dfd, name, O_RDONLY | O_DIRECTORY | O_NOFOLLOW | O_CLOEXEC);
+    if (fd < 0) return fail(VMIG_EIO, "prune: open %s: %s", name, errno_str(errno).c_str());
+    DIR* d = fdopendir(fd);
+    if (!d) { close(fd); return fail(VMIG_EIO, "prune: fdopendir %s: %s", name, errno_str(errno).c_str()); }
+    int rc = VMIG_OK;
+    while (struct dirent* de = readdir(d)) {
+        if (!strcmp(de->d_name, ".") || !strcmp(de->d_name, "..")) continue;
+        struct stat st;
+        if (fstatat(fd, de->d_name, &st, AT_SYMLINK_NOFOLLOW) != 0) continue;
+        if (S_ISDIR(st.st_mode)) { rc = rm_tree_at(fd, de->d_name, n); if (rc) break; }
+        else if (unlinkat(fd, de->d_name, 0) != 0 && errno != ENOENT) { rc = fail(VMIG_EIO, "prune: unlink %s: %s", de->d_name, errno_str(errno).c_str()); break; }
+        else (*n)++;
+    }
+    closedir(d);
+    if (rc) return rc;
+    if (unlinkat(dfd, name, AT_REMOVEDIR) != 0 && errno != ENOENT) return fail(VMIG_EIO, "prune: rmdir %s: %s", name, errno_str(errno).c_str());
+    (*n)++;
+    return VMIG_OK;
+}
+
+static int prune_dir(int dfd, const std::string& prefix, const std::unordered_set<std::string>& keep_dirs,
+                     const std::unordered_set<std::string>& keep_other, bool dry, uint64_t* n)
+{
+    DIR* d = fdopendir(dfd);                       // takes ownership of dfd
+    if (!d) { close(dfd); return fail(VMIG_EIO, "prune: fdopendir: %s", errno_str(errno).c_str()); }
+    int rc = VMIG_OK;
+    std::vector<std::string> names;
+    while (struct dirent* de = readdir(d)) if (strcmp(de->d_name, ".") && strcmp(de->d_name, "..")) names.push_back(de->d_name);
+    for (const auto& name : names) {
+        const std::string rel = prefix.empty() ? name : prefix + "/" + name;
+        struct stat st;
+        if (fstatat(dfd, name.c_str(), &st, AT_SYMLINK_NOFOLLOW) != 0) continue;
+        if (S_ISDIR(st.st_mode) && keep_dirs.count(rel)) {
+            int sub = openat(dfd, name.c_str(), O_RDONLY | O_DIRECTORY | O_NOFOLLOW | O_CLOEXEC);
+            if (sub < 0) { rc = fail(VMIG_EIO, "prune: open %s: %s", rel.c_str(), errno_str(errno).c_str()); break; }
+            rc = prune_dir(sub, rel, keep_dirs, keep_other, dry, n);
+            if (rc) break;
+            continue;
+        }
+        if (!S_ISDIR(st.st_mode) && keep_other.count(rel)) continue;
+        if (dry) { (*n)++; continue; }
+        if (S_ISDIR(st.st_mode)) { rc = rm_tree_at(dfd, name.c_str(), n); if (rc) break; }
+        else if (unlinkat(dfd, name.c_str(), 0) != 0 && errno != ENOENT) { rc = fail(VMIG_EIO, "prune: unlink %s: %s", rel.c_str(), errno_str(errno).c_str()); break; }
+        else (*n)++;
+    }
+    closedir(d);
+    return rc;
+}
+
+int prune_extras(const std::string& dst_root, const Manifest& m, bool dry_run, uint64_t* n_extras)
+{
+    std::unordered_set<std::string> keep_dirs, keep_other;
+    keep_dirs.reserve(m.dirs.size() * 2); keep_other.reserve((m.files.size() + m.symlinks.size() + m.specials.size()) * 2);
+    for (auto& e : m.dirs) keep_dirs.insert(e.rel);
+    for (auto& e : m.files) keep_other.insert(e.rel);
+    for (auto& e : m.symlinks) keep_other.insert(e.rel);
+    for (auto& e : m.specials) keep_other.insert(e.rel);
+    *n_extras = 0;
+    int fd = open(dst_root.c_str(), O_RDONLY | O_DIRECTORY | O_CLOEXEC);
+    if (fd < 0) return fail(VMIG_EIO, "prune: open %s: %s", dst_root.c_str(), errno_str(errno).c_str());
+    return prune_dir(fd, "", keep_dirs, keep_other, dry_run, n_extras);
 }
 
 }  // namespace vmig

@@ -70,6 +70,9 @@ int replay_metadata(const std::string& dst_root, const Manifest& m, const MetaPo
 int apply_file_meta(int fd, const std::string& path, const Entry& e, const MetaPolicy& pol);
 // VMIG_F_MOVE_SRC: unlink migrated source entries, children before parents; the root stays.
 int remove_source(const std::string& src_root, const Manifest& m);
+// VMIG_F_PRUNE: remove every destination entry the manifest does not list (directories recursively); entries are
+// handled by descriptor, symlinks are never followed.  dry_run only counts them (the verify pass uses that).
+int prune_extras(const std::string& dst_root, const Manifest& m, bool dry_run, uint64_t* n_extras);
 // Remove whatever non-directory sits at path (tar replaces existing entries).  ENOENT is fine.
 int unlink_if_exists(const std::string& path, bool* was_dir);
 

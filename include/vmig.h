@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define VMIG_ABI_VERSION 1
+#define VMIG_ABI_VERSION 2     /* 2: vmig_opts.lanes_per_gpu, vmig_stats.lanes_used/.pruned, VMIG_F_PRUNE, table format 02 */
 
 /* ---- error codes ------------------------------------------------------------------------ */
 #define VMIG_OK          0
@@ -81,6 +81,13 @@ const char* vmig_version(void);
                                            require its block hashes to equal the source's; with
                                            VMIG_F_MOVE_SRC the source is only unlinked if they do    */
 
+#define VMIG_F_PRUNE             0x40u  /* after the copy, remove every destination entry the source does not
+                                           have (files, symlinks, specials, whole directories).  tar never does
+                                           (default off); the final, paused pass of a hand-off needs it: a file
+                                           the tenant deleted or renamed since the live pass must not reappear
+                                           in the new container.  With VMIG_F_VERIFY the destination's entry set
+                                           is then re-walked and must equal the source's                       */
+
 typedef struct vmig_opts {
     uint32_t gpu_mask;         /* 0 = every initialised GPU; blocks are sharded across the set   */
     uint32_t block_bytes;      /* 0 -> 4 MiB (4194304); must be a multiple of 4096               */
@@ -108,6 +115,9 @@ typedef struct vmig_stats {
     double   ms_kernel;        /* sum of CUDA-event time of the hash kernels                     */
     uint32_t gpus_used;
     uint32_t lanes_used;       /* lanes the block list was sharded over (gpus_used * lanes_per_gpu) */
+    uint64_t pruned;           /* VMIG_F_PRUNE: destination entries removed                      */
+    uint64_t files_untrusted;  /* prior table given, but the destination file is no longer the one it was
+                                  written for (inode/ctime/size): copied in full, not patched    */
 } vmig_stats;
 
 /* ---- the hot path -------------------------------------------------------------------------- */
@@ -117,7 +127,8 @@ typedef struct vmig_stats {
  * xattrs are not; existing destination entries are overwritten, extras are never pruned).
  *   prior_table : nullable path of the block table describing what dst ALREADY holds (the prior
  *                 version).  Blocks whose XXH64 equals the prior entry are neither copied back
- *                 from HBM nor written (diff-skip).
+ *                 from HBM nor written (diff-skip) -- per file, and only while the destination file
+ *                 still is the one the table was written for (see "Block-table file").
  *   out_table   : nullable path; receives the block table of src (tmp + rename, after all data
  *                 writes completed).
  * Blocking; re-entrant; returns 0 or -VMIG_E*.  On error the destination may be partially
@@ -185,11 +196,17 @@ int vmig_link_probe(int gpu, uint64_t bytes, double gbs[4]);
 
 /* ---- block table + host-side helpers (no GPU needed) ---------------------------------------- */
 /* Block-table file, little-endian:
- *   char[8] "VMIGBT01"; u32 block_bytes; u32 algo (1 = XXH64 seed 0); u64 n_files; u64 n_blocks;
+ *   char[8] "VMIGBT02"; u32 block_bytes; u32 algo (1 = XXH64 seed 0); u64 n_files; u64 n_blocks;
  *   n_files x { u32 path_len; char path[path_len] (relative, no leading ./); u64 size;
- *               u64 first_block } sorted bytewise by path;
+ *               u64 first_block; u64 ino; i64 ctime_ns } sorted bytewise by path;
  *   u64 hashes[n_blocks].
  * A file of `size` bytes owns ceil(size/block_bytes) consecutive hashes (0 for an empty file).
+ * ino/ctime_ns identify the on-disk file the table speaks FOR: the destination file as the migration that wrote
+ * the table left it (the source file for a VMIG_F_HASH_ONLY table); 0/0 = unknown.  A later call that is handed
+ * the table as prior_table patches a destination file in place -- skipping blocks whose hash matches -- only
+ * while the file's inode, ctime and size still equal the record; otherwise (failed or partial earlier pass,
+ * out-of-band write, a table that belongs to another directory) that file is copied in full.  Format "VMIGBT01"
+ * (no ino/ctime_ns fields) is still read; its files are never patched in place.
  * Home in the reference: merges/<rs>/<rs>-<version>/ (internal/services/replicaset.go:681-704,
  * internal/version/merge.go:16). */
 typedef struct vmig_table_info {

@@ -3,7 +3,8 @@
 // vmig_handoff.go -- Go wiring for the "next" rows N1-N3 of SURVEY.md section 8f, on top of the cgo shim in
 // utils/copy_vmig.go.  New file: nothing in it exists in the reference; the comments name the reference lines a
 // maintainer changes to call it.  NOT COMPILED in this repository's image (no Go toolchain); the engine calls it
-// makes are the ones tests/test_gpu.py exercises through the Python mirror.
+// makes are the ones tests/test_gpu.py exercises through the Python mirror gpu-docker-api_b200/handoff.py, which is
+// kept line for line with this file (tests/test_gpu.py::test_handoff_*).
 package services
 
 /*
@@ -17,6 +18,7 @@ import "C"
 import (
 	"os"
 	"path/filepath"
+	"runtime"
 	"strings"
 	"unsafe"
 
@@ -70,7 +72,9 @@ func RollbackFromSnapshot(targetCtrVersionName, newContainer, seedTable string) 
 	if err := os.MkdirAll(filepath.Dir(newTable), 0755); err != nil {
 		return errors.Wrapf(err, "mkdir %s", filepath.Dir(newTable))
 	}
-	return errors.WithMessagef(utils.CopyDirDiff(data, upper, seedTable, newTable), "rollback to %s failed", targetCtrVersionName)
+	// verified + pruned: a seed table that no longer describes the layer is detected per file by the engine (inode/ctime
+	// recorded in the table) and that file is copied in full; the re-hash of the destination is the backstop
+	return errors.WithMessagef(utils.CopyDirDiffVerified(data, upper, seedTable, newTable), "rollback to %s failed", targetCtrVersionName)
 }
 
 // N2 -- HandoffCopy replaces utils.CopyOldMergedToNewContainerMerged in PatchContainer (replicaset.go:333):
@@ -121,6 +125,8 @@ func UsedBytes(volVersionName string) (int64, error) {
 	cs := C.CString(mountpoint)
 	defer C.free(unsafe.Pointer(cs))
 	var st C.vmig_stats
+	runtime.LockOSThread() // vmig_last_error() is thread-local: keep the call and the error fetch on one OS thread
+	defer runtime.UnlockOSThread()
 	if rc := C.vmig_manifest(cs, 0, 0, nil, &st); rc != 0 {
 		return 0, errors.Errorf("vmig_manifest(%s): %s: %s", mountpoint, C.GoString(C.vmig_strerror(rc)), C.GoString(C.vmig_last_error()))
 	}

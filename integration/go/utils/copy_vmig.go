@@ -10,18 +10,29 @@ package utils
 import "C"
 
 import (
+	"runtime"
 	"unsafe"
 
 	"github.com/ngaut/log"
 	"github.com/pkg/errors"
 )
 
+// vmigErr turns a return code into an error.  vmig_last_error() is thread-local and is read by a SEPARATE cgo call:
+// between two cgo calls the Go scheduler may move the goroutine to another OS thread, so every caller below brackets
+// "call + vmigErr" with runtime.LockOSThread()/UnlockOSThread() (lockedCall).
 func vmigErr(rc C.int, what string) error {
 	if rc == 0 {
 		return nil
 	}
 	return errors.Errorf("%s: %s (%d): %s", what, C.GoString(C.vmig_strerror(rc)), int(rc),
-		C.GoString(C.vmig_last_error())) // thread-local: cgo keeps the goroutine on its OS thread for the call
+		C.GoString(C.vmig_last_error()))
+}
+
+// lockedCall runs f (one libvmig call) and fetches its error text on the same OS thread.
+func lockedCall(what string, f func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	return vmigErr(f(), what)
 }
 
 // CopyDir replaces `sh -c "(cd src; tar c .) | (cd dest; tar x)"` (utils/copy.go:17-27).
@@ -29,7 +40,7 @@ func CopyDir(src, dest string) error {
 	cs, cd := C.CString(src), C.CString(dest)
 	defer C.free(unsafe.Pointer(cs))
 	defer C.free(unsafe.Pointer(cd))
-	return errors.Wrapf(vmigErr(C.vmig_copy_dir(cs, cd), "vmig_copy_dir"),
+	return errors.Wrapf(lockedCall("vmig_copy_dir", func() C.int { return C.vmig_copy_dir(cs, cd) }),
 		"vmig copy failed, src:%s, dest: %s", src, dest)
 }
 
@@ -41,9 +52,11 @@ func CopyDirDiff(src, dest, priorTable, outTable string) error {
 }
 
 // CopyDirDiffVerified additionally re-reads the destination through the GPU and compares block tables
-// (VMIG_F_VERIFY) before it reports success: for the pass after which the old container is deleted.
+// (VMIG_F_VERIFY), and removes every destination entry the source no longer has (VMIG_F_PRUNE: a file the tenant
+// deleted or renamed since an earlier pass must not reappear), before it reports success: for the pass after which
+// the old container is deleted, and for rollbacks onto a seeded layer.
 func CopyDirDiffVerified(src, dest, priorTable, outTable string) error {
-	return copyDirDiff(src, dest, priorTable, outTable, C.VMIG_F_VERIFY)
+	return copyDirDiff(src, dest, priorTable, outTable, C.VMIG_F_VERIFY|C.VMIG_F_PRUNE)
 }
 
 func copyDirDiff(src, dest, priorTable, outTable string, flags C.uint32_t) error {
@@ -62,13 +75,13 @@ func copyDirDiff(src, dest, priorTable, outTable string, flags C.uint32_t) error
 	var st C.vmig_stats
 	var o C.vmig_opts // zero value = defaults (all GPUs, 4 MiB blocks)
 	o.flags = flags
-	rc := C.vmig_migrate_tree(cs, cd, cp, co, &o, &st)
-	if rc == 0 {
-		log.Infof("vmig: %d bytes, %d/%d blocks skipped, %.2f GiB/s", uint64(st.bytes_total),
-			uint64(st.blocks_skipped), uint64(st.blocks_total),
-			float64(st.bytes_total)/float64(st.ns_total)*1e9/(1<<30))
+	err := lockedCall("vmig_migrate_tree", func() C.int { return C.vmig_migrate_tree(cs, cd, cp, co, &o, &st) })
+	if err == nil {
+		log.Infof("vmig: %d bytes, %d/%d blocks skipped, %d files copied in full (stale table), %d pruned, %.2f GiB/s",
+			uint64(st.bytes_total), uint64(st.blocks_skipped), uint64(st.blocks_total), uint64(st.files_untrusted),
+			uint64(st.pruned), float64(st.bytes_total)/float64(st.ns_total)*1e9/(1<<30))
 	}
-	return vmigErr(rc, "vmig_migrate_tree")
+	return err
 }
 
 // CopyOldMergedToNewContainerMerged (utils/copy.go:31-46): unchanged except for the callee.
@@ -89,5 +102,5 @@ func CopyOldMountPointToContainerMountPoint(oldVolume, newVolume string) error {
 	cs, cd := C.CString(src), C.CString(dst)
 	defer C.free(unsafe.Pointer(cs))
 	defer C.free(unsafe.Pointer(cd))
-	return errors.WithMessage(vmigErr(C.vmig_move_dir(cs, cd), "vmig_move_dir"), "moveData failed")
+	return errors.WithMessage(lockedCall("vmig_move_dir", func() C.int { return C.vmig_move_dir(cs, cd) }), "moveData failed")
 }

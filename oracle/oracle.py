@@ -253,7 +253,8 @@ def compare_trees(a, b, content: bool = True, mtime_ns: bool = False, ignore_roo
 
 
 # --------------------------------------------------------------------------- block table (restated)
-TABLE_MAGIC = b"VMIGBT01"
+TABLE_MAGIC = b"VMIGBT02"
+TABLE_MAGIC_V1 = b"VMIGBT01"
 
 
 def block_table_of_tree(root, block_bytes: int = BLOCK_BYTES):
@@ -278,12 +279,14 @@ def block_table_of_tree(root, block_bytes: int = BLOCK_BYTES):
 
 
 def read_table(path):
-    """Parse a block-table file written by the engine (format: include/vmig.h)."""
+    """Parse a block-table file written by the engine (format: include/vmig.h).  "VMIGBT02" carries the identity
+    (inode, ctime_ns) of the file each entry speaks for; "VMIGBT01" does not (identity (0, 0))."""
     raw = Path(path).read_bytes()
-    assert raw[:8] == TABLE_MAGIC, raw[:8]
+    assert raw[:8] in (TABLE_MAGIC, TABLE_MAGIC_V1), raw[:8]
+    v2 = raw[:8] == TABLE_MAGIC
     block_bytes, algo, n_files, n_blocks = struct.unpack_from("<IIQQ", raw, 8)
     off = 32
-    entries = []
+    entries, identity = [], []
     for _ in range(n_files):
         (plen,) = struct.unpack_from("<I", raw, off)
         off += 4
@@ -291,7 +294,12 @@ def read_table(path):
         off += plen
         size, first = struct.unpack_from("<QQ", raw, off)
         off += 16
+        if v2:
+            identity.append(struct.unpack_from("<Qq", raw, off))
+            off += 16
+        else:
+            identity.append((0, 0))
         entries.append((rel, size, first))
     hashes = np.frombuffer(raw, dtype="<u8", count=n_blocks, offset=off).copy()
     assert off + 8 * n_blocks == len(raw), (off, n_blocks, len(raw))
-    return {"block_bytes": block_bytes, "algo": algo, "entries": entries, "hashes": hashes}
+    return {"block_bytes": block_bytes, "algo": algo, "entries": entries, "identity": identity, "hashes": hashes}

@@ -69,6 +69,58 @@ def test_k1_ragged_blocks_vs_oracle(vm, orc):
     assert ms > 0
 
 
+def test_k1_chunk_and_ring_boundaries_vs_oracle(vm, orc):
+    """The kernel stages 1 KiB chunks through a 6-stage shared-memory ring: every length k*1024 + {-33..33 around the
+    stripe and chunk edges} for k = 1..14 (two wraps of the ring), plus the 6 KiB / 12 KiB wrap points +-1 and lengths that
+    end exactly where a stage is refilled.  One launch holds all of them next to full 4 MiB blocks (long and short
+    quads share a ring)."""
+    rng = np.random.default_rng(22)
+    deltas = (-33, -32, -31, -1, 0, 1, 31, 32, 33)
+    lens = sorted({k * 1024 + d for k in range(1, 15) for d in deltas} | {6 * 1024 * m + d for m in (1, 2, 3, 4) for d in (-1, 0, 1)}
+                  | {1025, 1055, 1056, 1057, 4 * MiB - 1024 - 1, 4 * MiB - 1024, 4 * MiB - 1024 + 1})
+    lens = np.array(lens + [4 * MiB] * 3, dtype=np.uint32)
+    rng.shuffle(lens)
+    offs = np.cumsum(np.concatenate([[3], lens[:-1].astype(np.uint64) + rng.integers(0, 17, len(lens) - 1).astype(np.uint64)])).astype(np.uint64)
+    buf = rng.integers(0, 256, int(offs[-1] + lens[-1]), dtype=np.uint8)
+    got, _ = vm.hash_blocks(buf, offs, lens)
+    want = orc.hash_blocks(buf, offs, lens)
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, [(int(i), int(lens[i])) for i in bad[:10]]
+
+
+def test_k1_repeated_under_load_from_another_stream(vm, orc):
+    """The stage hand-offs of K1 are shared-memory counters, not mbarriers, and the pre-multiplied bytes are refilled by
+    TMA without a proxy fence (csrc/vmig_kernels.cu): 20 launches back to back, while a second stream keeps every SM busy
+    with the 2.5 GiB resident pass (so the CTAs of the launch under test are descheduled and co-scheduled at random),
+    must all equal the oracle bit for bit."""
+    rng = np.random.default_rng(23)
+    lens = np.array([4 * MiB] * 24 + [4 * MiB - 1, 3 * MiB + 1025, 2 * MiB + 31, 1055, 6143, 6145, 12 * 1024 + 33, 0, 7],
+                    dtype=np.uint32)
+    offs = np.cumsum(np.concatenate([[0], lens[:-1].astype(np.uint64) + 1])).astype(np.uint64)
+    buf = rng.integers(0, 256, int(offs[-1] + lens[-1]), dtype=np.uint8)
+    want = orc.hash_blocks(buf, offs, lens)
+    r = vm.Resident(640, 4 * MiB)
+    stop, errs = threading.Event(), []
+
+    def load():
+        try:
+            r.fill(5); r.set_prior(None)
+            while not stop.is_set():
+                r.run(4)
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+    t = threading.Thread(target=load)
+    t.start()
+    try:
+        for rep in range(20):
+            got, _ = vm.hash_blocks(buf, offs, lens)
+            bad = np.nonzero(got != want)[0]
+            assert bad.size == 0, (rep, [(int(i), int(lens[i])) for i in bad[:10]])
+    finally:
+        stop.set(); t.join(); r.close()
+    assert not errs, errs
+
+
 def test_k1_many_small_blocks_dynamic_scheduling(vm, orc):
     """20 000 small blocks: several batches of 4096, work-stealing counter, zero-length blocks."""
     rng = np.random.default_rng(3)
@@ -589,7 +641,7 @@ def test_sharded_block_list_matches_oracle(vm, orc, shm_tmp, lanes):
 
 
 def test_full_size_resident_pass_properties(vm, orc):
-    """BASELINE config 2 size (10 GiB = 2 560 blocks resident in HBM): sampled blocks == oracle, the
+    """BASELINE config 2 size (10 GiB = 2 560 blocks resident in HBM): ALL 2 560 block hashes == oracle, the
     30 % mutation of config 4 is found exactly, and hashing is deterministic across passes."""
     n, bb = 2560, 4 * MiB
     r = vm.Resident(n, bb)
@@ -600,8 +652,18 @@ def test_full_size_resident_pass_properties(vm, orc):
         h1, surv = r.results()
         assert len(surv) == n
         words = bb // 8
-        for b in [0, 1, 147, 148, 1279, 2047, 2559]:
+        for b in [0, 1, 147, 148, 1279, 2047, 2559]:          # the device generator == the oracle's generator
             assert int(h1[b]) == orc.xxh64(orc.splitmix_bytes(0xB200, bb, first_word=b * words)), b
+        # EVERY one of the 2 560 hashes against the oracle: the resident bytes are downloaded 64 blocks at a time and
+        # hashed by oracle/xxh64_ref.c (10 GiB at ~7 GB/s on one core)
+        batch = np.empty(64 * bb, dtype=np.uint8)
+        boffs, blens = np.arange(64, dtype=np.uint64) * bb, [bb] * 64
+        for b0 in range(0, n, 64):
+            for j in range(64):
+                batch[j * bb:(j + 1) * bb] = r.download(b0 + j, bb)
+            want = orc.hash_blocks(batch, boffs, blens)
+            bad = np.nonzero(want != h1[b0:b0 + 64])[0]
+            assert bad.size == 0, (b0, bad[:8].tolist())
         r.run(2)
         h1b, _ = r.results()
         assert (h1 == h1b).all()
@@ -648,6 +710,219 @@ def test_full_size_rollback_diff_properties(vm, orc, shm_tmp):
         want = orc.hash_file(src / name)
         k = int(name[1:6]) * 256
         assert (t2[k:k + 256] == want).all() and (orc.hash_file(dst / name) == want).all()
+
+
+def test_c_abi_data_path_from_plain_c(vm, orc, shm_tmp):
+    """The C program of tests/c_abi_smoke.c (what cgo does: vmig_opts / vmig_stats by value, nullable tables, thread-local
+    errors, vmig_move_dir) against the GPU: copy + verify on 2 lanes, a no-op diff pass, then the move; the moved tree is
+    compared with the literal tar pipe's output."""
+    import subprocess
+    from test_host import build_c_abi_smoke, check_c_layout_line
+    exe = build_c_abi_smoke(vm, shm_tmp)
+    src, dst, moved, ref = shm_tmp / "s", shm_tmp / "d", shm_tmp / "m", shm_tmp / "ref"
+    src.mkdir(), dst.mkdir(), moved.mkdir(), ref.mkdir()
+    make_rich_tree(src, orc)
+    orc.ref_copy(src, ref)
+    r = subprocess.run([str(exe), str(src), str(dst), str(moved), str(shm_tmp / "t.vmig")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    check_c_layout_line(vm, r.stdout)
+    assert "copy ok" in r.stdout and "lanes=2" in r.stdout and "diff ok" in r.stdout and "move ok" in r.stdout, r.stdout
+    assert orc.compare_trees(ref, moved, ignore_root_mtime=True) == []
+    _, want = orc.block_table_of_tree(src)
+    assert (vm.table_hashes(shm_tmp / "t.vmig") == want).all()
+
+
+def test_prune_removes_what_the_source_no_longer_has(vm, orc, shm_tmp):
+    """VMIG_F_PRUNE (final pass of a hand-off): entries the tenant deleted or renamed between two passes must not
+    survive in the destination; without the flag they do (tar never prunes)."""
+    src, dst, ref = shm_tmp / "src", shm_tmp / "dst", shm_tmp / "ref"
+    src.mkdir(), dst.mkdir(), ref.mkdir()
+    make_rich_tree(src, orc)
+    (src / "gone_dir" / "deep").mkdir(parents=True)
+    (src / "gone_dir" / "deep" / "x.bin").write_bytes(orc.splitmix_bytes(9, 5 * MiB).tobytes())
+    (src / "old_name.bin").write_bytes(orc.splitmix_bytes(10, 4 * MiB + 5).tobytes())
+    os.symlink("old_name.bin", src / "gone_link")
+    vm.migrate_tree(src, dst, None, shm_tmp / "t1.vmig")
+    shutil.rmtree(src / "gone_dir")
+    os.rename(src / "old_name.bin", src / "new_name.bin")
+    os.unlink(src / "gone_link")
+    os.unlink(src / "sub" / "small.txt")              # one path of a hard-link pair
+    st = vm.migrate_tree(src, dst, shm_tmp / "t1.vmig", shm_tmp / "t2.vmig")           # tar semantics: extras stay
+    assert st["pruned"] == 0 and (dst / "gone_dir" / "deep" / "x.bin").exists() and (dst / "old_name.bin").exists()
+    st = vm.migrate_tree(src, dst, shm_tmp / "t2.vmig", shm_tmp / "t3.vmig", flags=vm.F_PRUNE | vm.F_VERIFY)
+    assert st["pruned"] == 6, st["pruned"]            # x.bin, deep, gone_dir, old_name.bin, gone_link, sub/small.txt
+    orc.ref_copy(src, ref)
+    assert orc.compare_trees(ref, dst) == []
+    # an entry planted in the destination alone is removed as well, whatever it is
+    (dst / "planted").mkdir(); (dst / "planted" / "f").write_bytes(b"x"); os.symlink("/etc", dst / "planted" / "esc")
+    st = vm.migrate_tree(src, dst, shm_tmp / "t3.vmig", None, flags=vm.F_PRUNE)
+    assert st["pruned"] == 3 and orc.compare_trees(ref, dst) == [] and os.path.isdir("/etc")
+
+
+def test_stale_prior_table_is_not_trusted(vm, orc, shm_tmp):
+    """The in-place diff path skips blocks whose source hash equals the prior table's entry, so the table must still
+    describe the destination FILE.  Tables record (inode, ctime) of the file they were written for: after an
+    out-of-band change of a destination file -- same size, mtime put back -- or with a table that belongs to another
+    directory, that file is copied in full and the destination still ends up equal to the source."""
+    src, dst = shm_tmp / "src", shm_tmp / "dst"
+    src.mkdir(), dst.mkdir()
+    for i in range(4):
+        (src / f"f{i}.bin").write_bytes(orc.splitmix_bytes(80 + i, 9 * MiB + i).tobytes())
+    vm.migrate_tree(src, dst, None, shm_tmp / "t1.vmig")
+    ident = orc.read_table(shm_tmp / "t1.vmig")["identity"]
+    for (ino, ct), name in zip(ident, sorted(os.listdir(dst))):
+        stt = os.stat(dst / name)
+        assert (ino, ct) == (stt.st_ino, stt.st_ctime_ns), name
+    # tamper with dst/f1.bin behind the engine's back: block 1 now differs from the source, size and mtime unchanged
+    before = os.stat(dst / "f1.bin")
+    _mutate(dst / "f1.bin", 1)
+    os.utime(dst / "f1.bin", ns=(before.st_atime_ns, before.st_mtime_ns))
+    st = vm.migrate_tree(src, dst, shm_tmp / "t1.vmig", shm_tmp / "t2.vmig")
+    assert st["files_untrusted"] == 1
+    assert st["blocks_total"] - st["blocks_skipped"] == 3          # f1.bin's three blocks travel, nothing else
+    for i in range(4):
+        assert (dst / f"f{i}.bin").read_bytes() == (src / f"f{i}.bin").read_bytes(), i
+    # a table written for ANOTHER directory is no licence to skip anything here
+    other = shm_tmp / "other"
+    other.mkdir()
+    vm.migrate_tree(src, other, None, shm_tmp / "t_other.vmig")
+    _mutate(dst / "f2.bin", 0)
+    st = vm.migrate_tree(src, dst, shm_tmp / "t_other.vmig", None)
+    assert st["files_untrusted"] == 4 and st["blocks_skipped"] == 0
+    assert (dst / "f2.bin").read_bytes() == (src / "f2.bin").read_bytes()
+    # format-01 tables (no identity) are read but never patched in place
+    t = orc.read_table(shm_tmp / "t2.vmig")
+    import struct
+    raw = b"VMIGBT01" + struct.pack("<IIQQ", t["block_bytes"], 1, len(t["entries"]), len(t["hashes"]))
+    for rel, size, first in t["entries"]:
+        raw += struct.pack("<I", len(rel)) + rel + struct.pack("<QQ", size, first)
+    (shm_tmp / "t_v1.vmig").write_bytes(raw + t["hashes"].astype("<u8").tobytes())
+    _mutate(dst / "f3.bin", 2)
+    st = vm.migrate_tree(src, dst, shm_tmp / "t_v1.vmig", None)
+    assert st["blocks_skipped"] == 0 and (dst / "f3.bin").read_bytes() == (src / "f3.bin").read_bytes()
+
+
+def _handoff(vm):
+    import importlib
+    return importlib.import_module(vm.__name__ + ".handoff")
+
+
+def test_handoff_two_pass_with_a_live_writer(vm, orc, shm_tmp):
+    """SURVEY.md §8f N2, the sequence of integration/go/services/vmig_handoff.go::HandoffCopy: pass 1 while a writer
+    keeps overwriting and appending to files of the source layer, pause (the writer stops), delete / rename in the
+    paused layer, pass 2 with prior = pass 1's table + VERIFY + PRUNE.  The destination must equal the literal tar
+    pipe's copy of the quiesced source, pass 2 must move only blocks of files the tenant touched, and the artefacts
+    must sit where setToMergeMap puts them (merges/<rs>/<rs>-<v>/, internal/services/replicaset.go:681-704)."""
+    ho = _handoff(vm)
+    old, new, ref = shm_tmp / "upper_old", shm_tmp / "upper_new", shm_tmp / "ref"
+    old.mkdir(), new.mkdir(), ref.mkdir()
+    sizes = {f"f{i:02d}.bin": (6 + i) * MiB + 17 * i for i in range(12)}
+    for name, n in sizes.items():
+        (old / name).write_bytes(orc.splitmix_bytes(700 + len(name) + n, n).tobytes())
+    hot = ["f00.bin", "f01.bin", "f02.bin"]                   # the tenant only touches these (and creates new ones)
+    stop, paused = threading.Event(), threading.Event()
+
+    def tenant():
+        rng = np.random.default_rng(1)
+        k = 0
+        while not stop.is_set():
+            name = hot[k % 3]
+            with open(old / name, "r+b") as f:
+                if k % 3 == 1:
+                    f.seek(0, 2); f.write(rng.integers(0, 256, 7000, dtype=np.uint8).tobytes())       # append
+                else:
+                    f.seek(int(rng.integers(0, sizes[name] - 4096))); f.write(rng.integers(0, 256, 4096, dtype=np.uint8).tobytes())
+            if k % 40 == 7:
+                (old / f"new{k}.log").write_bytes(b"log line\n" * (k + 1))
+            k += 1
+            time.sleep(0.0005)
+    th = threading.Thread(target=tenant)
+
+    def pause(name):
+        assert name == "rs-1"
+        stop.set(); th.join(); paused.set()
+        os.unlink(old / "f05.bin")                            # what the tenant did between the passes, seen only by pass 2
+        os.rename(old / "f06.bin", old / "renamed06.bin")
+
+    vm.set_resolver(container_upperdir=lambda n: str({"rs-1": old, "rs-2": new}[n]))
+    ho.set_merges_root(shm_tmp)
+    th.start()
+    try:
+        out = ho.HandoffCopy("rs-1", "rs-2", pause, lambda n: pytest.fail("resume called: the final pass failed"))
+    finally:
+        stop.set()
+        if th.is_alive():
+            th.join()
+        vm.set_resolver(None, None); ho.set_merges_root(None)
+    assert paused.is_set() and out["pass1"] is not None, out            # overwrite/append never shrinks a file: pass 1 succeeds
+    p2 = out["pass2"]
+    orc.ref_copy(old, ref)                                               # the reference's copy of the quiesced layer
+    assert orc.compare_trees(ref, new) == []
+    assert not (new / "f05.bin").exists() and not (new / "f06.bin").exists() and p2["pruned"] >= 2
+    nblk = lambda n: -(-n // (4 * MiB))                                  # noqa: E731
+    untouched = sum(nblk(sizes[f]) for f in sizes if f not in hot + ["f05.bin", "f06.bin"])
+    assert p2["blocks_skipped"] >= untouched, (p2["blocks_skipped"], untouched)      # cold files did not travel again
+    moved = p2["blocks_total"] - p2["blocks_skipped"]
+    budget = sum(nblk((old / f).stat().st_size) for f in hot) + nblk(sizes["f06.bin"]) + sum(1 for p in old.glob("new*.log"))
+    assert 0 < moved <= budget, (moved, budget)
+    assert p2["bytes_d2h"] < p2["bytes_total"] // 2
+    vdir = shm_tmp / "merges" / "rs" / "rs-2"
+    assert (vdir / "blocks.vmig").exists() and not (vdir / "blocks.vmig.pass1").exists()
+    _, want = orc.block_table_of_tree(old)
+    assert (vm.table_hashes(vdir / "blocks.vmig") == want).all()
+
+
+def test_handoff_live_pass_failure_falls_back_to_one_paused_pass(vm, orc, shm_tmp):
+    """A tenant that truncates a file under the reader makes the live pass fail with VMIG_ESRCCHANGED (or not, if the
+    race is lost); either way HandoffCopy ends with a verified paused pass and dst == src.  Then SnapshotVersion /
+    RollbackFromSnapshot (N1): the snapshot sits in merges/<rs>/<rs>-<v>/diff with its table, and a rollback onto a
+    layer seeded with another version moves only the differing blocks."""
+    ho = _handoff(vm)
+    old, new, ref = shm_tmp / "upper_old", shm_tmp / "upper_new", shm_tmp / "ref"
+    old.mkdir(), new.mkdir(), ref.mkdir()
+    for i in range(6):
+        (old / f"g{i}.bin").write_bytes(orc.splitmix_bytes(900 + i, 24 * MiB + i).tobytes())
+    stop = threading.Event()
+
+    def tenant():
+        k = 0
+        while not stop.is_set():
+            with open(old / "g0.bin", "r+b") as f:
+                f.truncate(1 * MiB if k % 2 == 0 else 24 * MiB)
+            k += 1
+    th = threading.Thread(target=tenant)
+
+    def pause(name):
+        stop.set(); th.join()
+        with open(old / "g0.bin", "r+b") as f:
+            f.truncate(24 * MiB)
+
+    vm.set_resolver(container_upperdir=lambda n: str({"rs-1": old, "rs-2": new, "rs-3": shm_tmp / "upper_3"}[n]))
+    ho.set_merges_root(shm_tmp)
+    th.start()
+    try:
+        out = ho.HandoffCopy("rs-1", "rs-2", pause, lambda n: pytest.fail("resume called"))
+        assert out["pass1"] is not None or out["pass1_error"] == vm.VMIG_ESRCCHANGED
+        orc.ref_copy(old, ref)
+        assert orc.compare_trees(ref, new) == []
+        # N1: snapshot version 2, create version 3 = version 2 with two blocks changed, roll a seeded layer back to 2
+        st = ho.SnapshotVersion("rs-2")
+        data, table = ho.snapshotPaths("rs-2")
+        assert data == shm_tmp / "merges" / "rs" / "rs-2" / "diff" and table.exists() and st["blocks_skipped"] == 0
+        assert orc.compare_trees(new, data) == []
+        up3 = shm_tmp / "upper_3"
+        up3.mkdir()
+        seed = shm_tmp / "seed3.vmig"
+        vm.migrate_tree(new, up3, None, seed)                  # the layer currently holds (a copy of) version 2 ...
+        _mutate(up3 / "g3.bin", 2)                             # ... then drifts behind the engine's back: g3 is untrusted,
+        st = ho.RollbackFromSnapshot("rs-2", "rs-3", seed)     # copied in full; the other five files do not travel
+        assert st["files_untrusted"] == 1 and st["blocks_total"] - st["blocks_skipped"] == 7
+        assert orc.compare_trees(data, up3) == []
+    finally:
+        stop.set()
+        if th.is_alive():
+            th.join()
+        vm.set_resolver(None, None); ho.set_merges_root(None)
 
 
 def test_smoke_entry_point():

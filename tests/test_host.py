@@ -33,20 +33,42 @@ def test_library_exports_every_declared_symbol(vm):
     assert "sm_100a" in vm.version()
 
 
-def test_c_abi_from_plain_c(vm, shm_tmp):
-    """include/vmig.h is plain C and the library links from C the way cgo would link it."""
+def build_c_abi_smoke(vm, out_dir):
     import subprocess
-    exe = shm_tmp / "c_abi_smoke"
+    exe = Path(out_dir) / "c_abi_smoke"
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(ROOT / "tests" / "c_abi_smoke.c"),
-                    "-o", str(exe), str(vm.LIB_PATH), "-Wl,-rpath," + str(vm.LIB_PATH.parent)], check=True)
-    src, dst = shm_tmp / "s", shm_tmp / "d"
-    (src / "sub").mkdir(parents=True), dst.mkdir()
+                    "-o", str(exe), str(vm.LIB_PATH), "-lpthread", "-Wl,-rpath," + str(vm.LIB_PATH.parent)], check=True)
+    return exe
+
+
+def check_c_layout_line(vm, stdout: str):
+    """The `layout` line of c_abi_smoke (sizeof/offsetof as the C compiler sees include/vmig.h) == the ctypes mirror."""
+    line = next(l for l in stdout.splitlines() if l.startswith("layout "))
+    f = dict(kv.split("=") for kv in line.split()[1:])
+    O, S, T = vm.Opts, vm.Stats, vm.TableInfo
+    assert f["opts"] == f"{ctypes.sizeof(O)}:" + ",".join(str(getattr(O, n).offset) for n in
+                                                        ("gpu_mask", "block_bytes", "streams_per_gpu", "flags", "io_threads", "lanes_per_gpu"))
+    assert f["stats"] == f"{ctypes.sizeof(S)}:" + ",".join(str(getattr(S, n).offset) for n in (
+        "bytes_total", "bytes_d2h", "blocks_skipped", "kernel_launches", "ns_total", "ns_table", "ms_kernel", "gpus_used", "lanes_used", "pruned"))
+    assert f["tinfo"] == f"{ctypes.sizeof(T)}:" + ",".join(str(getattr(T, n).offset) for n in ("algo", "n_files", "bytes_total"))
+    assert int(f["abi"]) == 2
+
+
+def test_c_abi_from_plain_c(vm, shm_tmp):
+    """include/vmig.h is plain C and the library links from C the way cgo would link it; the struct layout the C
+    compiler sees equals the ctypes mirror's; without a GPU the data-path call is refused before it touches dst."""
+    import subprocess
+    exe = build_c_abi_smoke(vm, shm_tmp)
+    src, dst, moved = shm_tmp / "s", shm_tmp / "d", shm_tmp / "m"
+    (src / "sub").mkdir(parents=True), dst.mkdir(), moved.mkdir()
     (src / "a").write_bytes(b"x" * 5000), (src / "sub" / "b").write_bytes(b"y" * 70)
-    r = subprocess.run([str(exe), str(src), str(dst)], capture_output=True, text=True, timeout=120)
+    r = subprocess.run([str(exe), str(src), str(dst), str(moved), str(shm_tmp / "t.vmig")], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
+    check_c_layout_line(vm, r.stdout)
     assert "files=2 bytes=5070 dir_size=5070" in r.stdout
     if "copy ok" in r.stdout:
-        assert (dst / "sub" / "b").read_bytes() == b"y" * 70
+        assert "diff ok skipped=2 of 2" in r.stdout and "move ok" in r.stdout
+        assert (moved / "sub" / "b").read_bytes() == b"y" * 70
     else:
         assert "no CPU fallback" in r.stdout and os.listdir(dst) == []
 
@@ -67,7 +89,7 @@ def test_source_side_path_safety_unit(shm_tmp):
 
 def test_struct_layouts_match_header(vm):
     assert ctypes.sizeof(vm.Opts) == 32
-    assert ctypes.sizeof(vm.Stats) == 18 * 8 + 8 + 8
+    assert ctypes.sizeof(vm.Stats) == 18 * 8 + 8 + 8 + 16
     assert ctypes.sizeof(vm.TableInfo) == 32
 
 
@@ -107,10 +129,13 @@ def test_datagen_matches_oracle_generator(vm, orc, shm_tmp):
         assert got.size == want.size and (got == want).all(), name
 
 
-def _write_table(path, entries, hashes, block_bytes=4 << 20):
-    raw = b"VMIGBT01" + struct.pack("<IIQQ", block_bytes, 1, len(entries), len(hashes))
-    for rel, size, first in entries:
+def _write_table(path, entries, hashes, block_bytes=4 << 20, identity=None):
+    """identity None -> format 01 (no file identity); else a list of (ino, ctime_ns) -> format 02."""
+    raw = (b"VMIGBT01" if identity is None else b"VMIGBT02") + struct.pack("<IIQQ", block_bytes, 1, len(entries), len(hashes))
+    for i, (rel, size, first) in enumerate(entries):
         raw += struct.pack("<I", len(rel)) + rel + struct.pack("<QQ", size, first)
+        if identity is not None:
+            raw += struct.pack("<Qq", *identity[i])
     raw += np.asarray(hashes, dtype="<u8").tobytes()
     Path(path).write_bytes(raw)
     return raw
@@ -125,6 +150,16 @@ def test_block_table_reader_accepts_good_and_rejects_bad(vm, orc, shm_tmp):
     assert info == {"block_bytes": 4 << 20, "algo": 1, "n_files": 3, "n_blocks": 4, "bytes_total": (8 << 20) + 101}
     assert list(vm.table_hashes(p)) == hashes
     assert orc.read_table(p)["entries"] == entries              # the oracle's parser agrees on the format
+    ident = [(12345, 1_700_000_000_123_456_789), (7, -5), (0, 0)]     # format 02: + (inode, ctime_ns) per file
+    raw2 = _write_table(shm_tmp / "t2.vmig", entries, hashes, identity=ident)
+    assert vm.table_info(shm_tmp / "t2.vmig") == info and list(vm.table_hashes(shm_tmp / "t2.vmig")) == hashes
+    t2 = orc.read_table(shm_tmp / "t2.vmig")
+    assert t2["entries"] == entries and t2["identity"] == ident
+    for bad in [raw2[:-1], raw2[:60], b"VMIGBT01" + raw2[8:], b"VMIGBT03" + raw2[8:]]:
+        (shm_tmp / "bad").write_bytes(bad)
+        with pytest.raises(vm.VmigError) as ei:
+            vm.table_info(shm_tmp / "bad")
+        assert ei.value.code == vm.VMIG_ETABLE
     for bad in [raw[:-1], b"XMIGBT01" + raw[8:], raw[:40], raw + b"\0" * 8]:
         (shm_tmp / "bad").write_bytes(bad)
         with pytest.raises(vm.VmigError) as ei:
