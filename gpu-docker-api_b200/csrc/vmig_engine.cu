@@ -16,6 +16,7 @@
 #include <fstream>
 #include <sstream>
 #include <algorithm>
+#include <unordered_map>
 #include <cstdlib>
 
 namespace vmig {
@@ -154,9 +155,24 @@ int Pipe::create_here(const DeviceInfo& d)
     CU_TRY(cudaSetDevice(d.dev));
     slots.resize(g_slots);
     const size_t cap = (size_t)slot_bytes + kTailPad;
+    // Which socket's DRAM holds the rings (first touch decides).  0 = the GPU's socket, 1 = the other socket(s),
+    // 2 = alternate slot by slot.  Four of the six DRAM passes a migrated byte makes touch a ring (IN write, H2D read,
+    // D2H write, OUT read); with everything on the GPU's socket that socket's memory controllers carry ~75 % of the
+    // traffic while the other one idles.  The OUT ring defaults to the writers' side (VMIG_BIND_WRITERS=2 puts them on
+    // the other socket): the D2H DMA crosses UPI once, the writers then read it locally.
+    const long in_node = env_long("VMIG_RING_IN_NODE", 0), out_node = env_long("VMIG_RING_OUT_NODE", 0);
+    auto place = [&](long mode, size_t idx) {
+        const bool far = mode == 1 || (mode == 2 && (idx & 1));
+        if (far) bind_thread_complement(d); else bind_thread(d);
+    };
+    size_t slot_idx = 0;
     for (auto& s : slots) {
+        place(in_node, slot_idx);
         { int rc = ring_alloc(&s.h_in, cap, &s.in_mapped); if (rc) return rc; }
+        place(out_node, slot_idx);
         { int rc = ring_alloc(&s.h_out, cap, &s.out_mapped); if (rc) return rc; }
+        bind_thread(d);
+        slot_idx++;
         CU_TRY(cudaMalloc((void**)&s.d_buf, cap));
         CU_TRY(cudaMemset(s.d_buf, 0, cap));
         CU_TRY(cudaHostAlloc((void**)&s.h_desc, kDescBytes, cudaHostAllocPortable));
@@ -193,6 +209,7 @@ struct DevPool {
     std::vector<Pipe*> free_pipes;
     uint32_t n_pipes = 0;
 };
+static cpu_set_t g_proc_cpus; static bool g_have_proc_cpus = false;     // affinity of the first thread that initialised the library
 static std::mutex g_mu;
 static std::condition_variable g_cv;
 static bool g_inited = false;
@@ -244,6 +261,8 @@ int ctx_init(uint32_t gpu_mask)
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return fail(VMIG_ENOGPU, "no CUDA device (%s); libvmig has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count 0"); }
     if (!g_inited) {
+        CPU_ZERO(&g_proc_cpus);
+        g_have_proc_cpus = sched_getaffinity(0, sizeof g_proc_cpus, &g_proc_cpus) == 0;
         struct rlimit rl;
         if (getrlimit(RLIMIT_NOFILE, &rl) == 0 && rl.rlim_cur < rl.rlim_max) { rl.rlim_cur = rl.rlim_max; setrlimit(RLIMIT_NOFILE, &rl); }
     }
@@ -420,7 +439,10 @@ int io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested,
 static void bind_thread_complement(const DeviceInfo& d) {
     if (d.cpus.empty()) return;
     cpu_set_t cur, set; CPU_ZERO(&cur); CPU_ZERO(&set);
-    if (sched_getaffinity(0, sizeof cur, &cur) != 0) return;
+    // complement within what the PROCESS may use (captured at init), not within this thread's present mask: the thread
+    // may already be bound to the GPU's CPUs
+    if (g_have_proc_cpus) cur = g_proc_cpus;
+    else if (sched_getaffinity(0, sizeof cur, &cur) != 0) return;
     for (int c = 0; c < CPU_SETSIZE; c++) if (CPU_ISSET(c, &cur)) CPU_SET(c, &set);
     for (int c : d.cpus) if (c < CPU_SETSIZE) CPU_CLR(c, &set);
     if (CPU_COUNT(&set) > 0) sched_setaffinity(0, sizeof set, &set);
@@ -506,6 +528,15 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
     // a time anyway (inode lock), so two writers on one file only queue up behind each other
     std::vector<std::unique_ptr<BQ<IoTask>>> write_qs;
     for (uint32_t t = 0; t < n_writers; t++) write_qs.push_back(std::make_unique<BQ<IoTask>>());
+    // write key -> writer: by the key's rank of first appearance IN THIS LANE, so a lane's files spread over all of its
+    // writers whatever their manifest indices are.  (Round 1 used key % n_writers: the whole-file split hands lane l of L
+    // the files l, l+L, l+2L, ... and with n_writers a multiple or divisor of L all of them landed on 1-3 writers -- the
+    // cause of the in-process multi-GPU collapse, 17.6 GiB/s on 8 GPUs: profiles/r02_lanes_vs_procs_1gpu.txt.)
+    std::unordered_map<uint32_t, uint32_t> key_rank;
+    if (!hash_only) {
+        key_rank.reserve(256);
+        for (const auto& b : blocks) { const uint32_t k = io->write_key(b); key_rank.emplace(k, (uint32_t)key_rank.size()); }
+    }
     BQ<Batch*> submit_q, hashwait_q, d2hwait_q;
     std::mutex done_mu; std::condition_variable done_cv; size_t batches_done = 0;
     std::mutex stat_mu;
@@ -713,7 +744,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
             }
             if (tasks.empty()) { finish_batch(b); continue; }
             b->writes_left.store((int)tasks.size());
-            for (auto& t : tasks) write_qs[io->write_key(blocks[t.i0]) % n_writers]->push(t);
+            for (auto& t : tasks) write_qs[key_rank[io->write_key(blocks[t.i0])] % n_writers]->push(t);
         }
     });
 
