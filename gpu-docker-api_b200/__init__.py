@@ -34,7 +34,7 @@ LIB_PATH = _HERE / "libvmig.so"
 VMIG_OK, VMIG_EINVAL, VMIG_ENOGPU, VMIG_ECUDA, VMIG_EIO = 0, -1, -2, -3, -4
 VMIG_ENOMEM, VMIG_ETABLE, VMIG_EFAULT, VMIG_ENOTDIR, VMIG_ESRCCHANGED, VMIG_EVERIFY = -5, -6, -7, -8, -9, -10
 F_MOVE_SRC, F_SKIP_HIDDEN_TOPDIRS, F_MTIME_NS, F_NO_METADATA, F_HASH_ONLY, F_VERIFY = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
-F_PRUNE = 0x40
+F_PRUNE, F_DIRECT_IO, F_CUFILE = 0x40, 0x80, 0x100
 BLOCK_BYTES = 4 << 20
 MOVE_DIR_FLAGS = F_MOVE_SRC | F_VERIFY          # what vmig_move_dir passes (include/vmig.h)
 
@@ -59,7 +59,7 @@ class Stats(C.Structure):
         "bytes_total", "bytes_h2d", "bytes_d2h", "bytes_written", "blocks_total", "blocks_skipped", "files", "dirs",
         "symlinks", "hardlinks", "specials", "kernel_launches", "ns_total", "ns_walk", "ns_plan", "ns_data",
         "ns_meta", "ns_table")] + [("ms_kernel", C.c_double), ("gpus_used", C.c_uint32), ("lanes_used", C.c_uint32), ("pruned", C.c_uint64),
-                                                    ("files_untrusted", C.c_uint64)]
+                                                    ("files_untrusted", C.c_uint64), ("files_direct", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}

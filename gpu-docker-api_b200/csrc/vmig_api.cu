@@ -7,6 +7,7 @@
 #include "vmig_kernels.cuh"
 #include "vmig_tree.h"
 #include "vmig_table.h"
+#include "vmig_cufile.h"
 
 #include <fcntl.h>
 #include <unistd.h>
@@ -32,12 +33,21 @@ public:
         bool inplace = false;            // diff path: destination file is the prior version, patched in place
         uint64_t dst_old_size = 0;
         uint64_t id_ino = 0; int64_t id_ctime_ns = 0;   // identity of the file the table will speak for (vmig_table.h)
+        bool s_direct = false, d_direct = false;         // this file's descriptor was opened with O_DIRECT
+        std::atomic<void*> s_cfh{nullptr}, d_cfh{nullptr};   // cuFile handles of sfd / dfd (VMIG_F_CUFILE)
     };
     std::string src_root, dst_root;
     int src_root_fd = -1;                // source files are opened beneath this descriptor, never by absolute path
     const Manifest* m = nullptr;
     MetaPolicy pol;
     bool hash_only = false;
+    bool direct = false;                 // VMIG_F_DIRECT_IO: O_DIRECT into / out of the pinned rings
+    bool cufile = false;                 // VMIG_F_CUFILE: file <-> HBM slot through libcufile (GPUDirect Storage)
+    std::atomic<uint64_t> n_direct{0};   // descriptors that really were opened O_DIRECT
+    static constexpr uint32_t kSector = 4096;
+    uint32_t slot_align() override { return direct || cufile ? kSector : 512; }
+    bool device_reads() override { return cufile; }
+    bool device_writes() override { return cufile && !hash_only; }
     long corrupt_block = -1;             // VMIG_CORRUPT_BLOCK test hook: flip one bit of this block on its way to disk
     std::unique_ptr<FS[]> fs;
     std::mutex stripes[64];
@@ -51,7 +61,9 @@ public:
             if (fd < 0) {
                 // the tenant may still be running on this layer: no symlink is followed and the root is never
                 // left (vmig_tree.h open_beneath); O_NONBLOCK so a FIFO swapped in cannot park a reader thread
-                int rc = open_beneath(src_root_fd, m->files[f].rel, O_RDONLY | O_NONBLOCK, &fd);
+                int rc = VMIG_EIO;
+                if (direct) { rc = open_beneath(src_root_fd, m->files[f].rel, O_RDONLY | O_NONBLOCK | O_DIRECT, &fd); s.s_direct = rc == VMIG_OK; }
+                if (rc) rc = open_beneath(src_root_fd, m->files[f].rel, O_RDONLY | O_NONBLOCK, &fd);     // the filesystem may refuse O_DIRECT
                 if (rc) return rc;
                 struct stat st;
                 if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
@@ -59,6 +71,13 @@ public:
                     return fail(VMIG_ESRCCHANGED, "%s is not a regular file any more", m->files[f].rel.c_str());
                 }
                 if (hash_only && st.st_nlink == 1) { s.id_ino = (uint64_t)st.st_ino; s.id_ctime_ns = (int64_t)st.st_ctim.tv_sec * 1000000000ll + st.st_ctim.tv_nsec; }
+                if (s.s_direct) n_direct++;
+                if (cufile) {
+                    void* h = nullptr;
+                    rc = cufile_handle_open(fd, &h);
+                    if (rc) { close(fd); return rc; }
+                    s.s_cfh.store(h, std::memory_order_release);
+                }
                 s.sfd.store(fd, std::memory_order_release);
             }
         }
@@ -72,16 +91,26 @@ public:
             fd = s.dfd.load(std::memory_order_acquire);
             if (fd < 0) {
                 const std::string p = pjoin(dst_root, m->files[f].rel);
+                const int dflag = direct && corrupt_block < 0 ? O_DIRECT : 0;
                 if (s.inplace) {
-                    fd = open(p.c_str(), O_WRONLY | O_CLOEXEC | O_NOFOLLOW);
+                    fd = open(p.c_str(), O_WRONLY | O_CLOEXEC | O_NOFOLLOW | dflag);
+                    if (fd < 0 && dflag && errno == EINVAL) fd = open(p.c_str(), O_WRONLY | O_CLOEXEC | O_NOFOLLOW); else s.d_direct = dflag != 0 && fd >= 0;
                 } else {
                     bool was_dir = false;
                     int rc = unlink_if_exists(p, &was_dir);     // tar replaces what is there
                     if (rc) return rc;
                     if (was_dir) return fail(VMIG_EIO, "%s: a directory is in the way of a regular file", p.c_str());
-                    fd = open(p.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_CLOEXEC | O_NOFOLLOW, 0600);
+                    fd = open(p.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_CLOEXEC | O_NOFOLLOW | dflag, 0600);
+                    if (fd < 0 && dflag && errno == EINVAL) fd = open(p.c_str(), O_WRONLY | O_CREAT | O_CLOEXEC | O_NOFOLLOW, 0600); else s.d_direct = dflag != 0 && fd >= 0;
                 }
                 if (fd < 0) return fail(VMIG_EIO, "open %s for writing: %s", p.c_str(), errno_str(errno).c_str());
+                if (s.d_direct) n_direct++;
+                if (cufile && !hash_only) {
+                    void* h = nullptr;
+                    int rc = cufile_handle_open(fd, &h);
+                    if (rc) { close(fd); return rc; }
+                    s.d_cfh.store(h, std::memory_order_release);
+                }
                 s.dfd.store(fd, std::memory_order_release);
             }
         }
@@ -90,15 +119,59 @@ public:
     int read_block(const BlockRef& b, uint8_t* dst) override {
         int fd; int rc = open_src(b.file, &fd);
         if (rc) return rc;
+        FS& s = fs[b.file];
+        // O_DIRECT: buffer, offset and length in whole sectors (the slot layout leaves the room; the device DMAs straight
+        // into the pinned ring); the file's last block is short, the read past EOF simply returns fewer bytes
+        const size_t want = s.s_direct ? (size_t)align_up(b.len, kSector) : b.len;
         size_t got = 0;
         while (got < b.len) {
-            ssize_t r = pread(fd, dst + got, b.len - got, (off_t)(b.file_off + got));
+            const size_t pos = s.s_direct ? (got & ~(size_t)(kSector - 1)) : got;      // after a short direct read: back to a sector boundary
+            ssize_t r = pread(fd, dst + pos, want - pos, (off_t)(b.file_off + pos));
             if (r < 0) { if (errno == EINTR) continue; return fail(VMIG_EIO, "pread %s: %s", m->files[b.file].rel.c_str(), errno_str(errno).c_str()); }
-            if (r == 0) return fail(VMIG_ESRCCHANGED, "%s shrank while being migrated (wanted %u bytes at %llu, got %zu)", m->files[b.file].rel.c_str(), b.len, (unsigned long long)b.file_off, got);
-            got += (size_t)r;
+            if (r == 0 || pos + (size_t)r <= got) return fail(VMIG_ESRCCHANGED, "%s shrank while being migrated (wanted %u bytes at %llu, got %zu)", m->files[b.file].rel.c_str(), b.len, (unsigned long long)b.file_off, got);
+            got = pos + (size_t)r;
         }
+        if (s.reads_left.fetch_sub(1) == 1) { close_src(s, fd); }
+        return VMIG_OK;
+    }
+    void close_src(FS& s, int fd) {
+        void* h = s.s_cfh.exchange(nullptr);
+        if (h) cufile_handle_close(h);
+        close(fd); s.sfd.store(-1);
+    }
+    // GPUDirect Storage: file -> HBM slot
+    int read_block_dev(const BlockRef& b, uint8_t* d_base, size_t d_off) override {
+        int fd; int rc = open_src(b.file, &fd);
+        if (rc) return rc;
         FS& s = fs[b.file];
-        if (s.reads_left.fetch_sub(1) == 1) { close(fd); s.sfd.store(-1); }
+        void* h = s.s_cfh.load(std::memory_order_acquire);
+        const size_t want = s.s_direct ? (size_t)align_up(b.len, kSector) : b.len;
+        size_t got = 0;
+        while (got < b.len) {
+            const size_t pos = s.s_direct ? (got & ~(size_t)(kSector - 1)) : got;
+            const ssize_t r = cufile_read(h, d_base, want - pos, (off_t)(b.file_off + pos), (off_t)(d_off + pos));
+            if (r < 0) return (int)r;
+            if (r == 0 || pos + (size_t)r <= got) return fail(VMIG_ESRCCHANGED, "%s shrank while being migrated (wanted %u bytes at %llu, got %zu)", m->files[b.file].rel.c_str(), b.len, (unsigned long long)b.file_off, got);
+            got = pos + (size_t)r;
+        }
+        if (s.reads_left.fetch_sub(1) == 1) close_src(s, fd);
+        return VMIG_OK;
+    }
+    // GPUDirect Storage: HBM slot -> file (surviving blocks only)
+    int write_block_dev(const BlockRef& b, const uint8_t* d_base, size_t d_off) override {
+        int fd; int rc = open_dst(b.file, &fd);
+        if (rc) return rc;
+        FS& s = fs[b.file];
+        void* h = s.d_cfh.load(std::memory_order_acquire);
+        const size_t want = s.d_direct ? (size_t)align_up(b.len, kSector) : b.len;
+        size_t put = 0;
+        while (put < b.len) {
+            const size_t pos = s.d_direct ? (put & ~(size_t)(kSector - 1)) : put;
+            const ssize_t w = cufile_write(h, d_base, want - pos, (off_t)(b.file_off + pos), (off_t)(d_off + pos));
+            if (w < 0) return (int)w;
+            if (w == 0 || pos + (size_t)w <= put) return fail(VMIG_EIO, "cuFileWrite %s: wrote 0 bytes", m->files[b.file].rel.c_str());
+            put = pos + (size_t)w;
+        }
         return VMIG_OK;
     }
     int write_block(const BlockRef& b, const uint8_t* src) override {
@@ -112,12 +185,17 @@ public:
             while (put1 < b.len) { ssize_t w = pwrite(fd, src + put1, b.len - put1, (off_t)(b.file_off + put1)); if (w <= 0) return fail(VMIG_EIO, "pwrite (fault hook)"); put1 += (size_t)w; }
             return VMIG_OK;
         }
+        // O_DIRECT: whole sectors out of the pinned ring; a short last block is written padded (whatever follows it in the
+        // slot) and block_done() cuts the file back to its size
+        const bool dio = fs[b.file].d_direct;
+        const size_t want = dio ? (size_t)align_up(b.len, kSector) : b.len;
         size_t put = 0;
         while (put < b.len) {
-            ssize_t w = pwrite(fd, src + put, b.len - put, (off_t)(b.file_off + put));
+            const size_t pos = dio ? (put & ~(size_t)(kSector - 1)) : put;
+            ssize_t w = pwrite(fd, src + pos, want - pos, (off_t)(b.file_off + pos));
             if (w < 0) { if (errno == EINTR) continue; return fail(VMIG_EIO, "pwrite %s: %s", m->files[b.file].rel.c_str(), errno_str(errno).c_str()); }
-            if (w == 0) return fail(VMIG_EIO, "pwrite %s: wrote 0 bytes", m->files[b.file].rel.c_str());
-            put += (size_t)w;
+            if (w == 0 || pos + (size_t)w <= put) return fail(VMIG_EIO, "pwrite %s: wrote 0 bytes", m->files[b.file].rel.c_str());
+            put = pos + (size_t)w;
         }
         return VMIG_OK;
     }
@@ -129,12 +207,13 @@ public:
         int fd; int rc = open_dst(b.file, &fd);      // also covers "every block was skipped"
         if (rc) return rc;
         const std::string p = pjoin(dst_root, e.rel);
-        if (s.inplace && s.dst_old_size != e.size && ftruncate(fd, (off_t)e.size) != 0) {
+        if (((s.inplace && s.dst_old_size != e.size) || (s.d_direct && (e.size & (kSector - 1)))) && ftruncate(fd, (off_t)e.size) != 0) {
             close(fd); return fail(VMIG_EIO, "ftruncate %s: %s", p.c_str(), errno_str(errno).c_str());
         }
         rc = apply_file_meta(fd, p, e, pol);
         struct stat ids;                             // nothing touches the file after this point: its ctime is final
         if (!rc && fstat(fd, &ids) == 0) { s.id_ino = (uint64_t)ids.st_ino; s.id_ctime_ns = (int64_t)ids.st_ctim.tv_sec * 1000000000ll + ids.st_ctim.tv_nsec; }
+        { void* h = s.d_cfh.exchange(nullptr); if (h) cufile_handle_close(h); }
         if (close(fd) != 0 && !rc) rc = fail(VMIG_EIO, "close %s: %s", p.c_str(), errno_str(errno).c_str());
         s.dfd.store(-1);
         return rc;
@@ -147,6 +226,8 @@ public:
     ~FileIO() { if (src_root_fd >= 0) close(src_root_fd); }
     void close_all(size_t n) {
         for (size_t i = 0; i < n; i++) {
+            void* h = fs[i].s_cfh.exchange(nullptr); if (h) cufile_handle_close(h);
+            h = fs[i].d_cfh.exchange(nullptr); if (h) cufile_handle_close(h);
             int a = fs[i].sfd.exchange(-1); if (a >= 0) close(a);
             int b = fs[i].dfd.exchange(-1); if (b >= 0) close(b);
         }
@@ -255,6 +336,8 @@ vmig_opts norm_opts(const vmig_opts* in) {
     vmig_opts o; memset(&o, 0, sizeof o);
     if (in) o = *in;
     if (!o.block_bytes) o.block_bytes = 4u << 20;
+    if (env_long("VMIG_DIRECT_IO", 0) == 1) o.flags |= VMIG_F_DIRECT_IO;
+    if (env_long("VMIG_CUFILE", 0) == 1) o.flags |= VMIG_F_CUFILE;
     return o;
 }
 
@@ -299,6 +382,9 @@ int migrate_tree_impl(const char* src_dir, const char* dst_dir, const char* prio
     FileIO io;
     io.src_root = src; io.dst_root = dst; io.m = &man; io.pol = default_meta_policy(o.flags); io.hash_only = hash_only;
     io.corrupt_block = env_long("VMIG_CORRUPT_BLOCK", -1);
+    io.direct = (o.flags & VMIG_F_DIRECT_IO) != 0;
+    io.cufile = (o.flags & VMIG_F_CUFILE) != 0;
+    if (io.cufile) { rc = cufile_open(); if (rc) return rc; }
     rc = io.open_root(); if (rc) return rc;
     io.fs.reset(new FileIO::FS[man.files.size() ? man.files.size() : 1]);
     std::vector<uint64_t> hashes(man.n_blocks, 0);
@@ -397,6 +483,8 @@ int migrate_tree_impl(const char* src_dir, const char* dst_dir, const char* prio
         // read the destination back through the same GPU path (hash only) and compare block tables
         FileIO vio;
         vio.src_root = dst; vio.dst_root = dst; vio.m = &man; vio.pol = io.pol; vio.hash_only = true;
+        vio.direct = io.direct;          // O_DIRECT re-read: what is verified is what the device holds, not the page cache
+        vio.cufile = io.cufile;
         vio.fs.reset(new FileIO::FS[man.files.size() ? man.files.size() : 1]);
         rc = vio.open_root(); if (rc) return rc;
         for (uint32_t f = 0; f < man.files.size(); f++) {
@@ -449,6 +537,7 @@ int migrate_tree_impl(const char* src_dir, const char* dst_dir, const char* prio
         rc = remove_source(src, man); if (rc) return rc;
     }
 
+    st.files_direct = io.n_direct.load();
     st.bytes_total = man.bytes_total; st.blocks_total = man.n_blocks;
     st.files = man.files.size(); st.dirs = man.dirs.size();
     st.ns_total = now_ns() - t_begin;
@@ -462,7 +551,7 @@ int migrate_tree_impl(const char* src_dir, const char* dst_dir, const char* prio
 extern "C" {
 
 int vmig_init(uint32_t gpu_mask) { return ctx_init(gpu_mask); }
-void vmig_shutdown(void) { ctx_shutdown(); }
+void vmig_shutdown(void) { ctx_shutdown(); cufile_shutdown(); }
 int vmig_device_count(void) { return ctx_device_count(); }
 const char* vmig_last_error(void) { return last_error_cstr(); }
 const char* vmig_version(void) { return "libvmig 0.1 (abi 1, sm_100a)"; }

@@ -4,6 +4,7 @@
 // (utils/copy.go:116); everything here is new design, there is no reference counterpart.
 #include "vmig_engine.h"
 #include "vmig_kernels.cuh"
+#include "vmig_cufile.h"
 
 #include <sched.h>
 #include <unistd.h>
@@ -75,6 +76,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_hash = nullptr, ev_d2h = nullptr;
     size_t in_mapped = 0, out_mapped = 0;   // > 0: ring is an mmap'ed huge-page region registered with CUDA
+    bool cf_registered = false;             // d_buf is registered with cuFile (GPUDirect Storage backends)
 };
 
 // Staging rings: 2 MiB-aligned anonymous memory with MADV_HUGEPAGE, faulted in, then page-locked
@@ -193,6 +195,7 @@ void Pipe::destroy()
     cudaSetDevice(dev.dev);
     for (auto& s : slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.cf_registered) { cufile_buf_deregister(s.d_buf); s.cf_registered = false; }
         ring_free(s.h_in, s.in_mapped); ring_free(s.h_out, s.out_mapped); cudaFree(s.d_buf); cudaFreeHost(s.h_desc); cudaFree(s.d_desc);
         cudaFreeHost(s.h_res); cudaFree(s.d_res); cudaFree(s.d_counter);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -500,7 +503,8 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
         if (err->compare_exchange_strong(expect, code)) { std::lock_guard<std::mutex> lk(*err_mu); *err_msg = last_error_cstr(); }
     };
 
-    // ---- plan: pack consecutive blocks into slot-sized batches, 512-B aligned
+    // ---- plan: pack consecutive blocks into slot-sized batches, 512-B aligned (4 KiB for O_DIRECT backends)
+    const uint32_t blk_align = std::max<uint32_t>(kBlockAlign, io->slot_align());
     std::vector<uint32_t> slot_off(blocks.size());
     std::vector<std::unique_ptr<Batch>> batches;
     {
@@ -509,7 +513,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
             auto b = std::make_unique<Batch>();
             b->b0 = i; size_t used = 0;
             while (i < blocks.size() && (i - b->b0) < kMaxBatchBlocks) {
-                const size_t need = align_up(std::max<uint32_t>(blocks[i].len, 1), kBlockAlign);
+                const size_t need = align_up(std::max<uint32_t>(blocks[i].len, 1), blk_align);
                 if (need > slot_bytes) { set_last_error("block of %u bytes exceeds the %u-byte staging slot (VMIG_SLOT_MB)", blocks[i].len, slot_bytes); set_err(VMIG_EINVAL); return VMIG_EINVAL; }
                 if (used + need > slot_bytes) break;
                 slot_off[i] = (uint32_t)used; used += need; i++;
@@ -551,6 +555,16 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
     };
     const bool direct_src = io->pinned_src(blocks[0]) != nullptr;
     const bool direct_dst = !hash_only && io->pinned_dst(blocks[0]) != nullptr;
+    // GPUDirect Storage backends: file <-> HBM slot without the pinned rings
+    const bool dev_src = !direct_src && io->device_reads();
+    const bool dev_dst = !hash_only && !direct_dst && io->device_writes();
+    if (dev_src || dev_dst) {
+        cudaSetDevice(pipe->dev.dev);
+        for (int s = 0; s < use_slots; s++) {
+            Slot& sl = pipe->slots[s];
+            if (!sl.cf_registered) { cufile_buf_register(sl.d_buf, (size_t)slot_bytes + kTailPad); sl.cf_registered = true; }
+        }
+    }
 
     // ---- stage 1: dispatcher -> read tasks
     std::thread dispatcher([&] {
@@ -580,13 +594,14 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
     for (uint32_t t = 0; t < n_readers; t++)
         readers.emplace_back([&] {
             if (bind_io) bind_thread(pipe->dev);
+            if (dev_src) cudaSetDevice(pipe->dev.dev);
             IoTask k;
             while (read_q.pop(&k)) {
                 Slot& sl = pipe->slots[k.batch->slot];
                 const uint64_t r0 = now_ns();
                 if (!err->load())
                     for (size_t i = k.i0; i < k.i1; i++) {
-                        int rc = io->read_block(blocks[i], sl.h_in + slot_off[i]);
+                        int rc = dev_src ? io->read_block_dev(blocks[i], sl.d_buf, slot_off[i]) : io->read_block(blocks[i], sl.h_in + slot_off[i]);
                         if (rc) { set_err(rc); break; }
                     }
                 rd_busy += now_ns() - r0;
@@ -615,7 +630,8 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
                 h2d += r.len;
             }
         } else {
-            CU_TRY(cudaMemcpyAsync(sl.d_buf, sl.h_in, b->bytes_used, cudaMemcpyHostToDevice, sl.stream));
+            // (GPUDirect Storage backends already put the bytes into the HBM slot on the reader threads)
+            if (!dev_src) CU_TRY(cudaMemcpyAsync(sl.d_buf, sl.h_in, b->bytes_used, cudaMemcpyHostToDevice, sl.stream));
             for (uint32_t i = 0; i < n; i++) h2d += blocks[b->b0 + i].len;
         }
         HashLaunch a;
@@ -630,7 +646,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
         CU_TRY(cudaMemcpyAsync(sl.h_res, sl.d_res, (size_t)n * 9, cudaMemcpyDeviceToHost, sl.stream));
         CU_TRY(cudaEventRecord(sl.ev_hash, sl.stream));
         uint64_t d2h = 0;
-        if (!has_prior && !hash_only) {       // every block survives: stream it back right away
+        if (!has_prior && !hash_only && !dev_dst) {       // every block survives: stream it back right away
             if (direct_dst) {
                 for (uint32_t i = 0; i < n; i++) {
                     const BlockRef& r = blocks[b->b0 + i];
@@ -675,7 +691,9 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
             if (fail_block >= 0 && (uint64_t)fail_block == r.table_idx) return fail(VMIG_EFAULT, "injected fault at block %ld (VMIG_FAIL_BLOCK)", fail_block);
             if (has_prior && !h_changed[i]) { b->survive[i] = 0; skipped++; }
         }
-        if (has_prior && !hash_only) {
+        if (dev_dst) {
+            for (uint32_t i = 0; i < n; i++) if (b->survive[i]) d2h += blocks[b->b0 + i].len;      // drained by the writers straight from HBM
+        } else if (has_prior && !hash_only) {
             uint32_t i = 0;
             while (i < n) {      // coalesce runs of adjacent survivors into one DMA
                 if (!b->survive[i] || !blocks[b->b0 + i].len) { i++; continue; }
@@ -715,7 +733,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
         Batch* b;
         while (d2hwait_q.pop(&b)) {
             Slot& sl = pipe->slots[b->slot];
-            if (!b->failed && !hash_only) {
+            if (!b->failed && !hash_only && !dev_dst) {
                 cudaError_t e = cudaEventSynchronize(sl.ev_d2h);
                 if (e != cudaSuccess) { fail(VMIG_ECUDA, "cudaEventSynchronize(d2h): %s", cudaGetErrorString(e)); set_err(VMIG_ECUDA); b->failed = true; }
             }
@@ -754,6 +772,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
         writers.emplace_back([&, t] {
             if (bind_io && bind_wr == 1) bind_thread(pipe->dev);
             else if (bind_io && bind_wr == 2) bind_thread_complement(pipe->dev);
+            if (dev_dst) cudaSetDevice(pipe->dev.dev);
             IoTask k;
             while (write_qs[t]->pop(&k)) {
                 Slot& sl = pipe->slots[k.batch->slot];
@@ -761,7 +780,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
                 const uint64_t w0 = now_ns();
                 for (size_t i = k.i0; i < k.i1; i++) {
                     if (err->load()) break;
-                    int rc = io->write_block(blocks[i], sl.h_out + slot_off[i]);
+                    int rc = dev_dst ? io->write_block_dev(blocks[i], sl.d_buf, slot_off[i]) : io->write_block(blocks[i], sl.h_out + slot_off[i]);
                     if (!rc) { wrote += blocks[i].len; rc = io->block_done(blocks[i], true); }
                     if (rc) { set_err(rc); break; }
                 }

@@ -40,6 +40,15 @@ public:
     // writes with the same key are issued by one writer thread, in order (a file takes writes from one
     // thread at a time anyway); backends without such a constraint spread the keys
     virtual uint32_t write_key(const BlockRef& b) { return b.file; }
+    // staging layout: every block starts at a multiple of this inside a slot (>= 512, a power of two).  O_DIRECT
+    // file I/O needs logical-sector alignment of buffer, offset and length: 4096.
+    virtual uint32_t slot_align() { return 512; }
+    // GPUDirect-Storage style backends move bytes between the file and the HBM slot themselves (no pinned ring, no
+    // cudaMemcpyAsync): read_block_dev fills d_base + d_off, write_block_dev drains it.  Called on reader / writer threads.
+    virtual bool device_reads()  { return false; }
+    virtual bool device_writes() { return false; }
+    virtual int  read_block_dev(const BlockRef&, uint8_t* /*d_base*/, size_t /*d_off*/) { return VMIG_EINVAL; }
+    virtual int  write_block_dev(const BlockRef&, const uint8_t* /*d_base*/, size_t /*d_off*/) { return VMIG_EINVAL; }
     // non-null: page-locked memory the DMA engines can use directly (no staging copy)
     virtual const uint8_t* pinned_src(const BlockRef&) { return nullptr; }
     virtual uint8_t*       pinned_dst(const BlockRef&) { return nullptr; }

@@ -88,6 +88,20 @@ const char* vmig_version(void);
                                            in the new container.  With VMIG_F_VERIFY the destination's entry set
                                            is then re-walked and must equal the source's                       */
 
+#define VMIG_F_DIRECT_IO         0x80u  /* disk-backed trees (the documented deployment keeps the Docker root on
+                                           xfs/LVM: reference docs/volume/volume-size-scale-en.md:5-21): source
+                                           files are read with O_DIRECT straight INTO the pinned staging ring and
+                                           destination files written with O_DIRECT straight OUT of it -- the NVMe
+                                           DMAs to/from the same page-locked memory the GPU's copy engines use, and
+                                           the page cache (two CPU copies per byte) is bypassed.  Falls back to
+                                           buffered I/O per file where the filesystem refuses O_DIRECT.  Env
+                                           VMIG_DIRECT_IO=1 sets it for every call.                              */
+#define VMIG_F_CUFILE            0x100u /* GPUDirect Storage ingest: source blocks are read with cuFileRead straight
+                                           into the HBM slot (no IN ring, no H2D copy); libcufile is dlopen()ed, the
+                                           call fails with VMIG_ENOTSUP-like VMIG_EINVAL if it is absent.  Without the
+                                           nvidia-fs kernel module libcufile runs in compatibility mode (POSIX read +
+                                           bounce buffer), which is functionally identical.  Env VMIG_CUFILE=1.     */
+
 typedef struct vmig_opts {
     uint32_t gpu_mask;         /* 0 = every initialised GPU; blocks are sharded across the set   */
     uint32_t block_bytes;      /* 0 -> 4 MiB (4194304); must be a multiple of 4096               */
@@ -118,6 +132,8 @@ typedef struct vmig_stats {
     uint64_t pruned;           /* VMIG_F_PRUNE: destination entries removed                      */
     uint64_t files_untrusted;  /* prior table given, but the destination file is no longer the one it was
                                   written for (inode/ctime/size): copied in full, not patched    */
+    uint64_t files_direct;     /* VMIG_F_DIRECT_IO / VMIG_F_CUFILE: descriptors (source + destination) the
+                                  filesystem really let us open with O_DIRECT                    */
 } vmig_stats;
 
 /* ---- the hot path -------------------------------------------------------------------------- */

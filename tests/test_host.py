@@ -89,7 +89,7 @@ def test_source_side_path_safety_unit(shm_tmp):
 
 def test_struct_layouts_match_header(vm):
     assert ctypes.sizeof(vm.Opts) == 32
-    assert ctypes.sizeof(vm.Stats) == 18 * 8 + 8 + 8 + 16
+    assert ctypes.sizeof(vm.Stats) == 18 * 8 + 8 + 8 + 24
     assert ctypes.sizeof(vm.TableInfo) == 32
 
 
