@@ -7,33 +7,40 @@
 //                    SURVEY.md Appendix A and checked bit-for-bit against oracle/xxh64_ref.c.
 // K2  diff_select  : ordered compaction of the changed flags into a survivor index list.
 //
-// Why K1 looks the way it does (measurements in profiles/r01_chain_probe.txt):
-//  * XXH64 is four dependent chains per block (acc = rotl(acc + x*P2, 31) * P1 per 8 input bytes
-//    per chain; rotl breaks associativity) so the only parallelism inside a block is 4.
-//    Parallelism comes from hashing many blocks at once: one QUAD (4 lanes) per block, 8 blocks
-//    per consumer warp, 4 consumer warps per CTA (one per SM sub-partition), one persistent CTA
-//    per SM -> 32 blocks in flight per SM.
-//  * With ~17 blocks per SM at the 10 GiB bench size the kernel is bound by the LATENCY of that
-//    chain, so the chain is what is engineered.  On B200 IMAD/IADD3/SHF have 4.4-cycle dependent
-//    latency but IMAD.WIDE / IMAD.HI (the 32x32->64 product a 64-bit multiply needs) take ~12.5
-//    cycles and occupy their unit ~7 cycles.  A round needs two 64-bit multiplies (x*P2 and
-//    rotl(..)*P1); only the second depends on the chain.  So the work is split by warp role:
-//      - PRODUCER warps (one per consumer warp) pull block indices from a global atomic counter,
-//        issue 1-D TMA bulk copies (cp.async.bulk global->shared, SASS UBLKCP) of 2 KiB chunks of
-//        each block into a 3-stage shared-memory ring, and when a chunk has landed PRE-MULTIPLY
-//        it in place (x -> x*P2, LDS.128/STS.128, fully parallel, off every chain);
-//      - CONSUMER warps run the chains: per 8 bytes one LDS.64, two funnel shifts, two IMADs
-//        and ONE IMAD.WIDE whose 64-bit addend carries x*P2 -- a 24-cycle round
-//        (nvcc's own lowering of the 64-bit expression: 42 cycles).
-//    The three hand-offs per stage (TMA landed / pre-multiplied / drained) are mbarriers; the
-//    steady state has no CTA-wide barrier.
-//  * Each chain lane walks an 8-byte column with a 32-byte stride; staging through shared memory
-//    turns that into contiguous 2 KiB HBM reads and conflict-free LDS.64 (quad slots are padded
-//    by 32 B so the 4 quads of a half-warp hit disjoint bank groups).
+// Why K1 looks the way it does (measurements in profiles/r01_chain_probe.txt, r01_k1_variants.txt):
+//  * XXH64 is four dependent chains per block (acc = rotl(acc + x*P2, 31) * P1 per 8 input bytes per chain; rotl
+//    breaks associativity) so the only parallelism inside a block is 4.  Parallelism comes from hashing many blocks at
+//    once: one QUAD (4 lanes) per block, 8 blocks per chain warp, 4 chain warps per CTA (one per SM sub-partition), one
+//    persistent CTA per SM -> 32 blocks in flight per SM, 4 736 per GPU.
+//  * With ~17 blocks per SM at the 10 GiB bench size the kernel is bound by the LATENCY of that chain, so the chain is
+//    what is engineered.  On B200 IMAD/IADD3/SHF have 4.4-cycle dependent latency but IMAD.WIDE / IMAD.HI (the 32x32->64
+//    product a 64-bit multiply needs) take ~12.5 cycles and occupy their unit ~7 cycles.  A round needs two 64-bit
+//    multiplies (x*P2 and rotl(..)*P1); only the second depends on the chain.  So the work is split over THREE warp
+//    roles per ring (a ring = the 8 quad slots of one chain warp; 12 warps per CTA):
+//      - the TMA warp pulls block indices (static first assignment, then a global atomic counter) and refills drained
+//        stages with 1-D TMA bulk copies (cp.async.bulk global->shared, SASS UBLKCP) of 1 KiB chunks of each block into
+//        a 6-STAGE shared-memory ring, one mbarrier arrive.expect_tx per stage, plus the stage's descriptors;
+//      - the PRE-MULTIPLY warp waits for the stage's mbarrier and replaces x by x*P2 in place (LDS.128 / IMAD.WIDE +
+//        2 IMAD / STS.128, fully parallel, off every chain);
+//      - the CHAIN warp (highest warp id = highest issue priority) runs the chains: per 8 bytes one LDS.64, two funnel
+//        shifts, two IMADs and ONE IMAD.WIDE whose 64-bit addend carries x*P2 -- a 24-cycle round in isolation (nvcc's
+//        own lowering of the 64-bit expression: 42 cycles), one predicate-free basic block per 1 KiB chunk.
+//    Hand-offs: "TMA landed" is an mbarrier (complete_tx needs one); "pre-multiplied" and "drained" are plain
+//    shared-memory counters written by one lane and polled with ld.volatile -- an mbarrier arrive/test/wait costs the
+//    issuing warp ~150 cycles of blocked issue (profiles/r01_k1_timeline_mbarrier.txt).  Ordering argument for the
+//    counters: the writer publishes with __syncwarp + __threadfence_block + st.volatile, the reader polls, then reads
+//    the data it guards through the same (generic) proxy; the async-proxy refill of a stage is issued only after the
+//    chain warp's hand-back has been observed, i.e. after every generic read of that stage has completed.  Evidence
+//    that this holds in practice: tests/test_gpu.py::test_k1_repeated_under_load_from_another_stream (20 launches under
+//    SM contention) and ::test_full_size_resident_pass_properties (all 2 560 hashes of the bench batch vs the oracle).
+//    There is one __syncthreads (after barrier init) and no CTA-wide barrier afterwards.
+//  * Each chain lane walks an 8-byte column with a 32-byte stride; staging through shared memory turns that into
+//    contiguous 1 KiB HBM reads (ncu: DRAM bytes == algorithmic bytes to 4 digits) and conflict-free LDS.64 (quad slots
+//    are padded by 32 B so the 4 quads of a half-warp hit disjoint bank groups).
 //  * No tensor cores: there is no contraction here, only 64-bit integer mul/add/rotate.
-//  * Work distribution: quad (cta c, warp w, quad q) starts on block c + G*(w + 4*q) so a small
-//    batch spreads over all SMs first, then over the 4 sub-partitions; afterwards quads pull
-//    indices from the atomic counter (ragged block lengths balance).
+//  * Work distribution: quad (cta c, ring w, quad q) starts on block c + G*(w + 4*q) so a small batch spreads over all
+//    SMs first, then over the 4 sub-partitions; afterwards quads pull indices from the atomic counter (ragged block
+//    lengths balance).
 #include "vmig_kernels.cuh"
 #include <atomic>
 
