@@ -304,15 +304,15 @@ int run_blocks(const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior,
             }
         }
     }
-    uint32_t readers, writers;
-    {
-        std::unordered_map<uint32_t, int> seen;                  // blocks are interleaved across <= 64 files
-        for (size_t i = 0; i < blocks.size() && i < 256; i++) seen[io->write_key(blocks[i])] = 1;
-        io_threads_default(&readers, &writers, o.io_threads, lanes, seen.size() >= 32, has_prior, hash_only);
-    }
     std::vector<Pipe*> pipes;
     rc = ctx_acquire_pipes(lane_devs, &pipes);
     if (rc) return rc;
+    uint32_t readers, writers;       // sized AFTER the pipes are checked out: the count of lanes in flight includes this call's
+    {
+        std::unordered_map<uint32_t, int> seen;                  // blocks are interleaved across <= 64 files
+        for (size_t i = 0; i < blocks.size() && i < 256; i++) seen[io->write_key(blocks[i])] = 1;
+        io_threads_default(&readers, &writers, o.io_threads, lanes, std::min(n_gpus, lanes), seen.size() >= 32, has_prior, hash_only);
+    }
     std::atomic<int> err{0}; std::string err_msg; std::mutex err_mu;
     std::vector<LaneStats> ls(lanes);
     std::vector<std::thread> th;

@@ -162,7 +162,8 @@ int Pipe::create_here(const DeviceInfo& d)
     // D2H write, OUT read); with everything on the GPU's socket that socket's memory controllers carry ~75 % of the
     // traffic while the other one idles.  The OUT ring defaults to the writers' side (VMIG_BIND_WRITERS=2 puts them on
     // the other socket): the D2H DMA crosses UPI once, the writers then read it locally.
-    const long in_node = env_long("VMIG_RING_IN_NODE", 0), out_node = env_long("VMIG_RING_OUT_NODE", 0);
+    const long in_node = env_long("VMIG_RING_IN_NODE", 0);
+    const long out_node = env_long("VMIG_RING_OUT_NODE", env_long("VMIG_BIND_WRITERS", 2) == 2 ? 1 : 0);      // +5..8 % end to end (profiles/r02_sweep_ring_placement.txt)
     auto place = [&](long mode, size_t idx) {
         const bool far = mode == 1 || (mode == 2 && (idx & 1));
         if (far) bind_thread_complement(d); else bind_thread(d);
@@ -404,7 +405,7 @@ void ctx_release_pipe(Pipe* p)
     p->destroy(); delete p;    // context was shut down underneath us
 }
 
-int io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested, size_t lanes, bool many_files,
+int io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested, size_t lanes, size_t n_gpus, bool many_files,
                        bool has_prior, bool hash_only)
 {
     long r = env_long("VMIG_READERS", 0), w = env_long("VMIG_WRITERS", 0);
@@ -412,27 +413,32 @@ int io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested,
     if (r <= 0 || w <= 0) {
         cpu_set_t cur; CPU_ZERO(&cur);
         long ncpu = sched_getaffinity(0, sizeof cur, &cur) == 0 ? CPU_COUNT(&cur) : sysconf(_SC_NPROCESSORS_ONLN);
-        // the host's copy capacity is shared by every migration running on it: this call's lanes, the
-        // lanes of other calls in flight in this process, and -- when the deployment runs one process per
-        // GPU, as bench.py under torchrun does -- whatever VMIG_IO_SHARE says (migrations expected at once)
-        long share = std::max<long>((long)lanes + std::max<long>(0, g_active_lanes.load()), env_long("VMIG_IO_SHARE", 1));
-        // measured on the 2-socket bench box (profiles/r01_e2e_threads.txt): the copy threads are
-        // memory-bound, more of them than ~8 readers + ~12 writers per GPU only adds contention
-        long budget = std::min<long>(24, std::max<long>(4, ncpu / share));
+        // The host's page-cache copy capacity is a property of the BOX, not of a lane: measured on the 2-socket bench box,
+        // ONE GPU is served best by ~20 copy threads in total however many lanes share it (8 readers + 12 writers; 40
+        // threads: 12.4 GiB/s instead of 19.3, 96 threads: 8.8 -- profiles/r02_sweep_lanes_1gpu.txt), and eight GPUs by
+        // ~13 per GPU (104 in total: 41.8 GiB/s; 64: 39.7, 160: 39.2 -- profiles/r01_e2e_rank_scaling.txt).  So the
+        // budget is per GPU in use and is DIVIDED among the lanes that share the box: this call's lanes, the lanes of other
+        // calls in flight in this process, and -- one process per GPU, as bench.py under torchrun runs -- whatever
+        // VMIG_IO_SHARE says (migrations expected at once).
+        const long other = std::max<long>(0, g_active_lanes.load() - (long)lanes);           // lanes of other calls in this process
+        const long share = std::max<long>((long)lanes + other, env_long("VMIG_IO_SHARE", 1));
+        const long gpus = std::max<long>(1, std::max<long>((long)n_gpus + (other > 0 ? other : 0), env_long("VMIG_IO_SHARE", 1)));
+        const long box = std::min<long>(std::max<long>(20, 13 * gpus), std::max<long>(4, ncpu * 7 / 8));
+        const long budget = std::max<long>(4, box / share);
         // few large files: the destination serialises per file, extra readers only steal memory
         // bandwidth from the writers; many files: reads are the longer pole
         if (hash_only) {
             // nothing is written: all of the budget reads (pread scales to ~16 threads on the bench box:
             // 28 GiB/s with 8 readers, 43.7 with 16, 34 with 24 -- profiles/r01_e2e_threads.txt)
-            if (r <= 0) r = std::max<long>(2, budget * 2 / 3);
+            if (r <= 0) r = std::max<long>(2, budget * 4 / 5);
             if (w <= 0) w = 1;
         } else if (has_prior) {
             // diff path: every block is read, only the changed ones are written
-            if (r <= 0) r = std::max<long>(2, budget / 2);
-            if (w <= 0) w = std::max<long>(2, budget / 2);
+            if (r <= 0) r = std::max<long>(2, budget * 3 / 5);
+            if (w <= 0) w = std::max<long>(2, budget * 3 / 5);
         } else {
-            if (r <= 0) r = std::max<long>(2, many_files ? budget / 2 : budget / 3);
-            if (w <= 0) w = std::max<long>(2, budget / 2);
+            if (r <= 0) r = std::max<long>(2, many_files ? budget / 2 : budget * 2 / 5);
+            if (w <= 0) w = std::max<long>(2, budget - r);
         }
     }
     *readers = (uint32_t)std::min<long>(r, 64); *writers = (uint32_t)std::min<long>(w, 64);

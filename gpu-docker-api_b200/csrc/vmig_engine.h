@@ -78,7 +78,7 @@ int  ctx_acquire_pipe(const DeviceInfo& d, Pipe** out);
 int  ctx_acquire_pipes(const std::vector<DeviceInfo>& lane_devs, std::vector<Pipe*>* out);
 void ctx_release_pipe(Pipe* p);
 uint32_t pipe_slot_bytes();
-int  io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested, size_t lanes, bool many_files,
+int  io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested, size_t lanes, size_t n_gpus, bool many_files,
                         bool has_prior, bool hash_only);
 
 // Run blocks[] through one GPU.  hashes_out[b.table_idx] receives every block's hash.
