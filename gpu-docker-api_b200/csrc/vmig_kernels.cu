@@ -43,6 +43,7 @@
 //    lengths balance).
 #include "vmig_kernels.cuh"
 #include <atomic>
+#include <cstdlib>
 
 namespace vmig {
 
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(3 * kWarps * 32, 1)
 xxh64_blocks_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ offs,
                     const uint32_t* __restrict__ lens, uint32_t n, uint64_t* __restrict__ hashes,
                     const uint64_t* __restrict__ prior, const uint8_t* __restrict__ prior_valid,
-                    uint8_t* __restrict__ changed, uint32_t* __restrict__ work_counter)
+                    uint8_t* __restrict__ changed, uint32_t* __restrict__ work_counter, uint32_t proxy_fence)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t warp_all = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -379,9 +380,11 @@ xxh64_blocks_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict
                 }
             }
             K1_TRACE(1, pm, 3);
-            // No fence.proxy.async here: the async-proxy (TMA) refill of these bytes is issued only after
+            // No fence.proxy.async by default: the async-proxy (TMA) refill of these bytes is issued only after
             // the chain warp has READ what is stored here and the TMA warp has seen its hand-back, so the
-            // stores are long performed; the fence cost this warp several hundred cycles per stage.
+            // stores are long performed.  VMIG_K1_PROXY_FENCE=1 puts the fence in (a warp-uniform kernel argument) so
+            // that its cost can be measured and the two variants compared bit for bit: profiles/r02_k1_proxy_fence.txt.
+            if (proxy_fence) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) { __threadfence_block(); sts_volatile(ready_cnt_s, pm + 1); }   // release: stage pm is consumable
             K1_TRACE(1, pm, 1);
@@ -570,8 +573,9 @@ cudaError_t launch_xxh64_blocks(const HashLaunch& a, int sm_count, cudaStream_t 
     // persistent grid: one CTA per SM, never more CTAs than blocks
     uint32_t grid = (uint32_t)sm_count;
     if (a.n < grid) grid = a.n;
+    static const uint32_t proxy_fence = [] { const char* v = getenv("VMIG_K1_PROXY_FENCE"); return (uint32_t)(v && *v == '1'); }();
     xxh64_blocks_kernel<<<grid, 3 * kWarps * 32, kSmemBytes, st>>>(a.base, a.offs, a.lens, a.n, a.hashes, a.prior,
-                                                              a.prior_valid, a.changed, a.work_counter);
+                                                              a.prior_valid, a.changed, a.work_counter, proxy_fence);
     return cudaGetLastError();
 }
 

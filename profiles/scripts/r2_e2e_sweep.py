@@ -23,8 +23,12 @@ VARIANTS = {
     "r4w6": {"VMIG_READERS": "4", "VMIG_WRITERS": "6"}, "r5w8": {"VMIG_READERS": "5", "VMIG_WRITERS": "8"},
     "r6w10": {"VMIG_READERS": "6", "VMIG_WRITERS": "10"}, "r8w10": {"VMIG_READERS": "8", "VMIG_WRITERS": "10"},
     "r3w5": {"VMIG_READERS": "3", "VMIG_WRITERS": "5"}, "r2w3": {"VMIG_READERS": "2", "VMIG_WRITERS": "3"},
+    "r8w14": {"VMIG_READERS": "8", "VMIG_WRITERS": "14"}, "r9w12": {"VMIG_READERS": "9", "VMIG_WRITERS": "12"},
+    "r7w12": {"VMIG_READERS": "7", "VMIG_WRITERS": "12"}, "r8w16": {"VMIG_READERS": "8", "VMIG_WRITERS": "16"},
     "r10w16": {"VMIG_READERS": "10", "VMIG_WRITERS": "16"}, "r12w20": {"VMIG_READERS": "12", "VMIG_WRITERS": "20"},
     "outfar_r10w16": {"VMIG_RING_OUT_NODE": "1", "VMIG_READERS": "10", "VMIG_WRITERS": "16"},
+    "direct": {"VMIG_DIRECT_IO": "1"}, "cufile": {"VMIG_CUFILE": "1"}, "direct_cufile": {"VMIG_DIRECT_IO": "1", "VMIG_CUFILE": "1"},
+    "outnear": {"VMIG_RING_OUT_NODE": "0"}, "wboth": {"VMIG_BIND_WRITERS": "0"},
     "slots8": {"VMIG_SLOTS": "8"}, "slot16mb": {"VMIG_SLOT_MB": "16", "VMIG_SLOTS": "32"}, "slot8mb": {"VMIG_SLOT_MB": "8", "VMIG_SLOTS": "32"},
 }
 

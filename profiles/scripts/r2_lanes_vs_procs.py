@@ -94,6 +94,14 @@ def main():
                 print(f"[{kk} processes, one lane each; VMIG_IO_SHARE={kk}]", flush=True)
                 run_procs(kk, min(gpus, kk), fpl, reps, dict(env0, VMIG_IO_SHARE=str(kk)))
                 kk *= 2
+        if "konly" in variants:              # just the full lane count: K lanes in one process against K processes
+            inproc(k, dict(env0, VMIG_TRACE="1"), "")
+            print(f"[{k} processes, one lane each; VMIG_IO_SHARE={k}]", flush=True)
+            run_procs(k, min(gpus, k), fpl, reps, dict(env0, VMIG_IO_SHARE=str(k)))
+        for v in variants:                   # rNwM: N readers + M writers per lane, in-process
+            if v.startswith("r") and "w" in v and v[1].isdigit():
+                r, w = v[1:].split("w")
+                inproc(k, dict(env0, VMIG_READERS=r, VMIG_WRITERS=w), f", {r} readers + {w} writers per lane")
         if "mbind" in variants:
             inproc(k, dict(env0, VMIG_RING_MBIND="1"), ", VMIG_RING_MBIND=1")
         if "nobind" in variants:
