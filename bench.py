@@ -122,6 +122,40 @@ def dist_setup():
     return rank, world, local, barrier, allmax
 
 
+def mem_budget_bytes() -> int:
+    """Bytes this process may still put into tmpfs + page-locked memory: the tightest of the cgroup limit (v2 or v1),
+    MemAvailable and the free space of the bench directory.  A GPU box that runs out of memory is lost, not slowed."""
+    cands = []
+    for lim, cur in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                     ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            l = Path(lim).read_text().strip()
+            if l != "max" and int(l) < (1 << 60):
+                cands.append(int(l) - int(Path(cur).read_text().strip()))
+        except (OSError, ValueError):
+            pass
+    try:
+        for line in Path("/proc/meminfo").read_text().splitlines():
+            if line.startswith("MemAvailable:"):
+                cands.append(int(line.split()[1]) * 1024)
+    except OSError:
+        pass
+    try:
+        st = os.statvfs(shm_base())
+        cands.append(st.f_bavail * st.f_frsize)
+    except OSError:
+        pass
+    return min(cands) if cands else 1 << 62
+
+
+def require_memory(need: int, what: str) -> None:
+    have = mem_budget_bytes()
+    if need > have * 0.85:
+        raise SystemExit(f"bench.py: {what} needs {need / GiB:.0f} GiB of tmpfs + pinned memory but only {have / GiB:.0f} GiB "
+                         f"are available to this container (cgroup limit / MemAvailable / {shm_base()}); refusing to run it "
+                         "rather than drive the box out of memory")
+
+
 def fresh_dir(p: Path) -> Path:
     shutil.rmtree(p, ignore_errors=True)
     p.mkdir(parents=True)
@@ -266,6 +300,7 @@ def run_reference(args) -> None:
         n_par, seed0 = args.callers, 50
     base = fresh_dir(shm_base() / "vmig_bench_ref")
     mnt = None
+    require_memory(int(2.1 * n_par * per_tree_files * GiB) if cfg != "2B" else 22 * GiB, f"reference arm, config {cfg}")
     try:
         srcs, nbytes = [], 0
         if mode == "mv":
@@ -434,6 +469,10 @@ def main() -> None:
         clocks = ClockSampler(gpu)
 
         # ---------------- build the workload and the step
+        need_gib = {"1": 4, "2A": 32 * (world if world > 1 else 1) + (22 * world if world > 1 and not args.no_sharded else 0), "2B": 32,
+                    "3": 204, "4": 104, "5": 21 * args.callers + 4}[cfg]
+        if rank == 0:
+            require_memory(need_gib * GiB, f"config {cfg}")
         if cfg in ("2A", "2B"):
             if active:
                 src = base / "src"
