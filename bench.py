@@ -96,6 +96,15 @@ class ClockSampler:
                 "samples": len(sm), "note": "sampled while the end-to-end steps ran; the path is host/PCIe-bound, so SM clocks idle low between the per-slot hash launches"}
 
 
+_CPU_WAIT = [lambda: None]       # set by dist_setup: a barrier that parks ranks on the CPU (gloo), not inside an NCCL kernel
+
+
+def cpu_barrier() -> None:
+    """Long waits (other ranks idle while rank 0 drives every GPU from one process) must not sit in an NCCL barrier:
+    its kernel spins on the waiting rank's GPU and would time-slice against rank 0's hash kernels there."""
+    _CPU_WAIT[0]()
+
+
 def dist_setup():
     """(rank, world, local_rank, barrier, allmax).  torch.distributed (NCCL) is plumbing only."""
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -109,6 +118,9 @@ def dist_setup():
         torch.cuda.set_device(local)
     dist.init_process_group("nccl" if use_cuda else "gloo")
     dev = torch.device("cuda", local) if use_cuda else torch.device("cpu")
+    import datetime
+    cpu_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(minutes=30))
+    _CPU_WAIT[0] = lambda: dist.barrier(group=cpu_group)
 
     def barrier():
         dist.barrier()
@@ -630,7 +642,7 @@ def main() -> None:
         # ---------------- N>1, config 2A: rank 0 alone drives all N GPUs with ONE call (north-star split)
         sharded = None
         if world > 1 and cfg == "2A" and not args.no_sharded:
-            barrier()
+            cpu_barrier()
             if rank == 0:
                 shutil.rmtree(base / "dst", ignore_errors=True)
                 big = base / "src_all"
@@ -650,7 +662,7 @@ def main() -> None:
                            "api": f"ONE vmig_migrate_tree call in rank 0's process, gpu_mask=0x{all_mask:x}: {10 * world} x 1 GiB sharded "
                                   "across the GPUs (whole files per lane); the other ranks idle", "steps": len(ts), "warmup": 2}
                 shutil.rmtree(big, ignore_errors=True), shutil.rmtree(base / "dst_all", ignore_errors=True)
-            barrier()
+            cpu_barrier()
 
         if rank == 0:
             n_trees = world if not solo else 1
@@ -699,7 +711,7 @@ def main() -> None:
             pass
     if world > 1:
         import torch.distributed as dist
-        dist.barrier()
+        cpu_barrier()
         dist.destroy_process_group()
 
 

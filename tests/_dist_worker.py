@@ -11,6 +11,7 @@ rank, world, local, barrier, allmax = bench.dist_setup()
 barrier()
 slowest = allmax(1.0 + rank)              # max over ranks, as the timing rules require
 barrier()
+bench.cpu_barrier()                      # the CPU-side (gloo) wait used while rank 0 drives all GPUs alone
 plan = bench.rank_plan("2A", local, world, world)
 solo = {c: bench.rank_plan(c, local, world, world) for c in ("1", "2B", "3", "4", "5")}
 out = {"rank": rank, "world": world, "local": local, "max": slowest, "gpu_mask": plan["own_mask"],
