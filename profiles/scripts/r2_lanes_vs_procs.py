@@ -18,8 +18,14 @@ def role_inproc(k, gpus, fpl, reps):
     vm = g.load_pkg()
     mask = (1 << gpus) - 1
     vm.init(mask)
-    src = BASE / "src" if k > 1 else BASE / "src" / "s0"
-    nbytes = (k if k > 1 else 1) * fpl * GiB
+    # a tree holding exactly k of the subtrees (hard links: no extra memory)
+    src = BASE / f"src_first{k}"
+    if not src.exists():
+        for i in range(k):
+            (src / f"s{i}").mkdir(parents=True)
+            for f in sorted((BASE / "src" / f"s{i}").iterdir()):
+                os.link(f, src / f"s{i}" / f.name)
+    nbytes = k * fpl * GiB
     lpg = max(1, k // gpus)
     for rep in range(reps + 1):
         dst = BASE / "dst_in"; shutil.rmtree(dst, ignore_errors=True); dst.mkdir()
