@@ -194,7 +194,7 @@ int walk_tree(const std::string& src_root, uint32_t block_bytes, bool skip_hidde
                 if (r) { std::lock_guard<std::mutex> lk(bad_mu); if (!bad.load()) { bad_msg = last_error_cstr(); bad.store(r); } return; }
             }
         };
-        const size_t nth = std::min<size_t>(8, top.size());
+        const size_t nth = std::min<size_t>((size_t)std::max<long>(1, env_long("VMIG_WALK_THREADS", 8)), top.size());
         if (nth <= 1) work();
         else { std::vector<std::thread> th; for (size_t t = 0; t < nth; t++) th.emplace_back(work); for (auto& t : th) t.join(); }
         close(rfd2);
