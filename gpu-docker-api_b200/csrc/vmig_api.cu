@@ -35,6 +35,7 @@ public:
         uint64_t id_ino = 0; int64_t id_ctime_ns = 0;   // identity of the file the table will speak for (vmig_table.h)
         bool s_direct = false, d_direct = false;         // this file's descriptor was opened with O_DIRECT
         std::atomic<void*> s_cfh{nullptr}, d_cfh{nullptr};   // cuFile handles of sfd / dfd (VMIG_F_CUFILE)
+        std::atomic<bool> wrote{false};                  // at least one block of the file was written in this call
     };
     std::string src_root, dst_root;
     int src_root_fd = -1;                // source files are opened beneath this descriptor, never by absolute path
@@ -52,6 +53,13 @@ public:
     std::unique_ptr<FS[]> fs;
     std::mutex stripes[64];
 
+    // libcufile refuses descriptors whose open flags include O_NOFOLLOW / O_NONBLOCK ("unsupported file open flags"),
+    // which is exactly how the safe opens below are made, and F_SETFL cannot clear O_NOFOLLOW.  The descriptor already
+    // refers to the checked regular file, so it is re-opened through /proc/self/fd with plain flags.
+    static int reopen_plain(int fd, int flags) {
+        char p[64]; snprintf(p, sizeof p, "/proc/self/fd/%d", fd);
+        return open(p, flags | O_CLOEXEC);
+    }
     int open_src(uint32_t f, int* out) {
         FS& s = fs[f];
         int fd = s.sfd.load(std::memory_order_acquire);
@@ -73,6 +81,9 @@ public:
                 if (hash_only && st.st_nlink == 1) { s.id_ino = (uint64_t)st.st_ino; s.id_ctime_ns = (int64_t)st.st_ctim.tv_sec * 1000000000ll + st.st_ctim.tv_nsec; }
                 if (s.s_direct) n_direct++;
                 if (cufile) {
+                    const int nfd = reopen_plain(fd, O_RDONLY | (s.s_direct ? O_DIRECT : 0));
+                    if (nfd < 0) { const int e = errno; close(fd); return fail(VMIG_EIO, "reopen %s for cuFile: %s", m->files[f].rel.c_str(), errno_str(e).c_str()); }
+                    close(fd); fd = nfd;
                     void* h = nullptr;
                     rc = cufile_handle_open(fd, &h);
                     if (rc) { close(fd); return rc; }
@@ -106,6 +117,9 @@ public:
                 if (fd < 0) return fail(VMIG_EIO, "open %s for writing: %s", p.c_str(), errno_str(errno).c_str());
                 if (s.d_direct) n_direct++;
                 if (cufile && !hash_only) {
+                    const int nfd = reopen_plain(fd, O_WRONLY | (s.d_direct ? O_DIRECT : 0));
+                    if (nfd < 0) { const int e = errno; close(fd); return fail(VMIG_EIO, "reopen %s for cuFile: %s", p.c_str(), errno_str(e).c_str()); }
+                    close(fd); fd = nfd;
                     void* h = nullptr;
                     int rc = cufile_handle_open(fd, &h);
                     if (rc) { close(fd); return rc; }
@@ -162,6 +176,7 @@ public:
         int fd; int rc = open_dst(b.file, &fd);
         if (rc) return rc;
         FS& s = fs[b.file];
+        s.wrote.store(true, std::memory_order_relaxed);
         void* h = s.d_cfh.load(std::memory_order_acquire);
         const size_t want = s.d_direct ? (size_t)align_up(b.len, kSector) : b.len;
         size_t put = 0;
@@ -177,6 +192,7 @@ public:
     int write_block(const BlockRef& b, const uint8_t* src) override {
         int fd; int rc = open_dst(b.file, &fd);
         if (rc) return rc;
+        fs[b.file].wrote.store(true, std::memory_order_relaxed);
         if (corrupt_block >= 0 && (uint64_t)corrupt_block == b.table_idx && b.len) {
             const uint8_t bad = src[0] ^ 1u;           // what VMIG_F_VERIFY exists to catch
             if (pwrite(fd, &bad, 1, (off_t)b.file_off) != 1) return fail(VMIG_EIO, "pwrite (fault hook)");
@@ -210,7 +226,10 @@ public:
         if (((s.inplace && s.dst_old_size != e.size) || (s.d_direct && (e.size & (kSector - 1)))) && ftruncate(fd, (off_t)e.size) != 0) {
             close(fd); return fail(VMIG_EIO, "ftruncate %s: %s", p.c_str(), errno_str(errno).c_str());
         }
-        rc = apply_file_meta(fd, p, e, pol);
+        // a patched-in-place file none of whose blocks changed and whose metadata is already right is not touched at all:
+        // its ctime -- by which the block table knows it -- stays what the table recorded
+        const bool untouched = s.inplace && !s.wrote.load() && s.dst_old_size == e.size && file_meta_matches(fd, e, pol);
+        rc = untouched ? VMIG_OK : apply_file_meta(fd, p, e, pol);
         struct stat ids;                             // nothing touches the file after this point: its ctime is final
         if (!rc && fstat(fd, &ids) == 0) { s.id_ino = (uint64_t)ids.st_ino; s.id_ctime_ns = (int64_t)ids.st_ctim.tv_sec * 1000000000ll + ids.st_ctim.tv_nsec; }
         { void* h = s.d_cfh.exchange(nullptr); if (h) cufile_handle_close(h); }

@@ -283,6 +283,19 @@ int make_dirs(const std::string& dst_root, const Manifest& m)
     return VMIG_OK;
 }
 
+bool file_meta_matches(int fd, const Entry& e, const MetaPolicy& pol)
+{
+    if (pol.no_metadata) return true;
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0) return false;
+    struct timespec ts[2];
+    fill_times(e, pol, ts);
+    if (pol.keep_atime) return false;                       // move semantics restore atime too: always apply
+    if (pol.is_root && (st.st_uid != e.uid || st.st_gid != e.gid)) return false;
+    if ((st.st_mode & 07777) != eff_mode(e, pol)) return false;
+    return st.st_mtim.tv_sec == ts[1].tv_sec && st.st_mtim.tv_nsec == ts[1].tv_nsec;
+}
+
 int apply_file_meta(int fd, const std::string& path, const Entry& e, const MetaPolicy& pol)
 {
     if (pol.no_metadata) return VMIG_OK;

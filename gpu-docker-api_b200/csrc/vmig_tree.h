@@ -66,6 +66,9 @@ int make_dirs(const std::string& dst_root, const Manifest& m);
 // Symlinks, specials, hard links and empty regular files; then directory metadata bottom-up.
 int replay_metadata(const std::string& dst_root, const Manifest& m, const MetaPolicy& pol,
                     uint64_t* n_symlinks, uint64_t* n_hardlinks, uint64_t* n_specials);
+// True if the open file already carries the owner/mode/mtime apply_file_meta would give it (then it is left alone: a
+// diff pass that skips every block of a file must not move its ctime, the block table identifies files by it).
+bool file_meta_matches(int fd, const Entry& e, const MetaPolicy& pol);
 // Apply owner/mode/mtime to an open regular file (fd) or to a path (fd < 0).
 int apply_file_meta(int fd, const std::string& path, const Entry& e, const MetaPolicy& pol);
 // VMIG_F_MOVE_SRC: unlink migrated source entries, children before parents; the root stays.

@@ -57,7 +57,10 @@ def make_rich_tree(root: Path, orc, seed: int = 5, big: int = (9 << 20) + 777):
     os.link(root / "sub" / "small.txt", root / "a_hard2")
     os.mkfifo(root / "fifo")
     if os.geteuid() == 0:
-        os.mknod(root / "whiteout", 0o020000 | 0o644, os.makedev(0, 0))   # overlay2 whiteout
+        try:
+            os.mknod(root / "whiteout", 0o020000 | 0o644, os.makedev(0, 0))   # overlay2 whiteout
+        except PermissionError:       # an overlayfs mount refuses to create its own whiteout marker by hand
+            os.mknod(root / "whiteout", 0o020000 | 0o644, os.makedev(1, 3))
         os.chown(root / "sub", 1234, 4321)
         os.chown(root / "sub" / "small.txt", 1000, 1000)
         os.lchown(root / "lnk", 42, 43)

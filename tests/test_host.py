@@ -58,7 +58,9 @@ def test_c_abi_from_plain_c(vm, shm_tmp):
     """include/vmig.h is plain C and the library links from C the way cgo would link it; the struct layout the C
     compiler sees equals the ctypes mirror's; without a GPU the data-path call is refused before it touches dst."""
     import subprocess
-    exe = build_c_abi_smoke(vm, shm_tmp)
+    import tempfile
+    exe_dir = Path(tempfile.mkdtemp(prefix="vmig_cabi_"))          # /dev/shm may be mounted noexec
+    exe = build_c_abi_smoke(vm, exe_dir)
     src, dst, moved = shm_tmp / "s", shm_tmp / "d", shm_tmp / "m"
     (src / "sub").mkdir(parents=True), dst.mkdir(), moved.mkdir()
     (src / "a").write_bytes(b"x" * 5000), (src / "sub" / "b").write_bytes(b"y" * 70)
