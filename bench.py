@@ -528,8 +528,9 @@ def main() -> None:
                 assert (vm.table_hashes(base / "v1.vmig") == v1_want).all(), "cfg4: prior table != oracle table of v1"
 
                 def step(i):
-                    if i > 0:
-                        flip_blocks(dst, changed, GiB // BLOCK)                     # back to v1 (the table still describes it)
+                    if i > 0:                       # outside the timed region: put dst back to v1 and re-take v1's table
+                        flip_blocks(dst, changed, GiB // BLOCK)                     # (a table names the files it speaks for by inode +
+                        vm.hash_tree(dst, base / "v1.vmig", gpu_mask=all_mask)       # ctime; the flips moved the ctimes)
                     t0 = time.perf_counter()
                     st = vm.migrate_tree(src, dst, base / "v1.vmig", base / "v2.vmig", gpu_mask=all_mask, lanes_per_gpu=lanes)
                     dt = time.perf_counter() - t0

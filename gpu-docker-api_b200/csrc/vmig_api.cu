@@ -573,7 +573,7 @@ int vmig_init(uint32_t gpu_mask) { return ctx_init(gpu_mask); }
 void vmig_shutdown(void) { ctx_shutdown(); cufile_shutdown(); }
 int vmig_device_count(void) { return ctx_device_count(); }
 const char* vmig_last_error(void) { return last_error_cstr(); }
-const char* vmig_version(void) { return "libvmig 0.1 (abi 1, sm_100a)"; }
+const char* vmig_version(void) { return "libvmig 0.2 (abi 2, sm_100a)"; }
 const char* vmig_strerror(int code)
 {
     switch (code) {

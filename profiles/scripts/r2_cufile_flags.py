@@ -1,24 +1,45 @@
-"""Which open(2) flags does cuFileHandleRegister accept on this box?  (round 2, N4)  python profiles/scripts/r2_cufile_flags.py [dir=/tmp]"""
-import ctypes as C, os, sys, tempfile
-lib = C.CDLL("libcufile.so.0")
-class Err(C.Structure): _fields_ = [("err", C.c_int), ("cu_err", C.c_int)]
-class Descr(C.Structure): _fields_ = [("type", C.c_int), ("fd", C.c_int), ("pad", C.c_int), ("fs_ops", C.c_void_p)]
-lib.cuFileDriverOpen.restype = Err
-lib.cuFileHandleRegister.restype = Err
-lib.cuFileHandleRegister.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Descr)]
-e = lib.cuFileDriverOpen(); print("cuFileDriverOpen:", e.err, e.cu_err)
-d = sys.argv[1] if len(sys.argv) > 1 else "/tmp"
-p = os.path.join(d, "cufile_flag_probe.bin"); open(p, "wb").write(b"x" * 8192)
-combos = {"O_RDONLY": os.O_RDONLY, "O_RDONLY|O_DIRECT": os.O_RDONLY | os.O_DIRECT, "O_RDONLY|O_NONBLOCK": os.O_RDONLY | os.O_NONBLOCK,
-          "O_RDONLY|O_NOFOLLOW": os.O_RDONLY | os.O_NOFOLLOW, "O_RDONLY|O_CLOEXEC": os.O_RDONLY | os.O_CLOEXEC,
-          "O_WRONLY": os.O_WRONLY, "O_WRONLY|O_DIRECT": os.O_WRONLY | os.O_DIRECT, "O_RDWR": os.O_RDWR, "O_RDWR|O_DIRECT": os.O_RDWR | os.O_DIRECT}
-for name, fl in combos.items():
-    try:
-        fd = os.open(p, fl)
-    except OSError as ex:
-        print(f"{name:24s} open failed: {ex}"); continue
-    h = C.c_void_p(); ds = Descr(1, fd, 0, None)
-    r = lib.cuFileHandleRegister(C.byref(h), C.byref(ds))
-    print(f"{name:24s} F_GETFL=0o{__import__('fcntl').fcntl(fd, __import__('fcntl').F_GETFL):o}  cuFileHandleRegister err={r.err}")
-    os.close(fd)
-os.unlink(p)
+"""Which descriptors does cuFileHandleRegister accept on this box?  (round 2, N4)
+  python profiles/scripts/r2_cufile_flags.py [dir ...]      default: /tmp /dev/shm
+Runs twice: stock configuration, then CUFILE_ENV_PATH_JSON pointing at a json that forces the compatibility mode."""
+import ctypes as C, fcntl, json, os, subprocess, sys, tempfile
+
+def probe(dirs):
+    lib = C.CDLL("libcufile.so.0")
+    class Err(C.Structure): _fields_ = [("err", C.c_int), ("cu_err", C.c_int)]
+    class Descr(C.Structure): _fields_ = [("type", C.c_int), ("fd", C.c_int), ("pad", C.c_int), ("fs_ops", C.c_void_p)]
+    lib.cuFileDriverOpen.restype = Err
+    lib.cuFileHandleRegister.restype = Err
+    lib.cuFileHandleRegister.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Descr)]
+    e = lib.cuFileDriverOpen(); print("cuFileDriverOpen:", e.err, e.cu_err, flush=True)
+    for d in dirs:
+        p = os.path.join(d, "cufile_flag_probe.bin"); open(p, "wb").write(b"x" * 8192)
+        fs = subprocess.run(["stat", "-f", "-c", "%T", d], capture_output=True, text=True).stdout.strip()
+        for name, fl in {"O_RDONLY": os.O_RDONLY, "O_RDONLY|O_DIRECT": os.O_RDONLY | os.O_DIRECT, "O_RDWR|O_DIRECT": os.O_RDWR | os.O_DIRECT,
+                         "O_RDONLY|O_NOFOLLOW": os.O_RDONLY | os.O_NOFOLLOW, "O_WRONLY": os.O_WRONLY}.items():
+            try:
+                fd = os.open(p, fl)
+            except OSError as ex:
+                print(f"{d} ({fs}) {name:22s} open failed: {ex}"); continue
+            h = C.c_void_p(); ds = Descr(1, fd, 0, None)
+            r = lib.cuFileHandleRegister(C.byref(h), C.byref(ds))
+            print(f"{d} ({fs}) {name:22s} F_GETFL=0o{fcntl.fcntl(fd, fcntl.F_GETFL):o}  cuFileHandleRegister err={r.err}", flush=True)
+            os.close(fd)
+        os.unlink(p)
+
+if len(sys.argv) > 1 and sys.argv[1] == "--child":
+    probe(sys.argv[2:]); sys.exit(0)
+dirs = sys.argv[1:] or ["/tmp", "/dev/shm"]
+work = tempfile.mkdtemp(prefix="cufile_probe_")
+for label, env in (("stock configuration", {}), ("forced compatibility mode", None)):
+    e = dict(os.environ)
+    if env is None:
+        cfg = {"logging": {"dir": work, "level": "INFO"}, "properties": {"allow_compat_mode": True, "force_compat_mode": True, "use_poll_mode": False},
+               "fs": {"generic": {"posix_unaligned_writes": True}}}
+        jp = os.path.join(work, "cufile.json"); json.dump(cfg, open(jp, "w"))
+        e["CUFILE_ENV_PATH_JSON"] = jp
+    print(f"== {label}", flush=True)
+    subprocess.run([sys.executable, __file__, "--child"] + dirs, env=e, cwd=work)
+for f in sorted(os.listdir(work)):
+    if f.startswith("cufile") and f.endswith(".log"):
+        print(f"== {f} (tail)"); print("".join(open(os.path.join(work, f), errors="replace").readlines()[-25:]))
+print("nvidia-fs module:", "present" if os.path.exists("/proc/driver/nvidia-fs") else "absent", "| lsmod:", subprocess.run("lsmod | grep -c nvidia", shell=True, capture_output=True, text=True).stdout.strip())
