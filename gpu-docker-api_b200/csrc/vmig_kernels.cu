@@ -570,9 +570,15 @@ cudaError_t launch_xxh64_blocks(const HashLaunch& a, int sm_count, cudaStream_t 
     }
     e = cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
-    // persistent grid: one CTA per SM, never more CTAs than blocks
+    // persistent grid: one CTA per SM for a large batch.  A small batch (the streaming engine launches once per staging
+    // slot: 8 blocks) gets one CTA per FOUR blocks, not per block: the first assignment puts block c + G*(ring + 4*quad) on
+    // CTA c, so with G = ceil(n/4) every CTA runs one block on each of its four rings (one per SM sub-partition) -- the
+    // chains do not share an issue port, the launch takes exactly as long (one block's chain latency), and it occupies a
+    // quarter of the SMs: 16 slots in flight need 32 SMs instead of 128, so several lanes (or a tenant's kernels) fit
+    // beside them instead of queueing (profiles/r02_sweep_lanes_1gpu.txt: 55 ms of hash latency with 4 lanes).
     uint32_t grid = (uint32_t)sm_count;
-    if (a.n < grid) grid = a.n;
+    const uint32_t want = (a.n + 3u) / 4u;
+    if (want < grid) grid = want ? want : 1u;
     static const uint32_t proxy_fence = [] { const char* v = getenv("VMIG_K1_PROXY_FENCE"); return (uint32_t)(v && *v == '1'); }();
     xxh64_blocks_kernel<<<grid, 3 * kWarps * 32, kSmemBytes, st>>>(a.base, a.offs, a.lens, a.n, a.hashes, a.prior,
                                                               a.prior_valid, a.changed, a.work_counter, proxy_fence);
