@@ -534,19 +534,41 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
     const int use_slots = max_slots ? (int)std::min<size_t>(max_slots, pipe->slots.size()) : (int)pipe->slots.size();
     for (int s = 0; s < use_slots; s++) free_slots.push(s);     // one side stream per slot in use
     BQ<IoTask> read_q;
-    // one queue per writer, keyed by destination file: a file accepts writes from one thread at
-    // a time anyway (inode lock), so two writers on one file only queue up behind each other
-    std::vector<std::unique_ptr<BQ<IoTask>>> write_qs;
-    for (uint32_t t = 0; t < n_writers; t++) write_qs.push_back(std::make_unique<BQ<IoTask>>());
-    // write key -> writer: by the key's rank of first appearance IN THIS LANE, so a lane's files spread over all of its
-    // writers whatever their manifest indices are.  (Round 1 used key % n_writers: the whole-file split hands lane l of L
-    // the files l, l+L, l+2L, ... and with n_writers a multiple or divisor of L all of them landed on 1-3 writers -- the
-    // cause of the in-process multi-GPU collapse, 17.6 GiB/s on 8 GPUs: profiles/r02_lanes_vs_procs_1gpu.txt.)
-    std::unordered_map<uint32_t, uint32_t> key_rank;
+    // Writers.  A destination file takes writes from one thread at a time anyway (inode lock), so two writers on one file
+    // only queue up behind each other: writes are queued PER FILE and any idle writer takes the next file that has work and
+    // is not being written right now.  (Round 1 pinned file -> writer by `file % n_writers`: the whole-file split hands
+    // lane l of L the files l, l+L, ... and they all landed on 1-3 writers -- the in-process multi-GPU collapse, 17.6 GiB/s
+    // on 8 GPUs, profiles/r02_lanes_vs_procs_1gpu.txt.  Pinning by rank fixed that but left 10 files on 7 writers with
+    // three writers carrying two files while four idled half the time: profiles/r02_lanes_vs_procs_8gpu.txt.)
+    std::unordered_map<uint32_t, uint32_t> key_rank;         // write key -> dense rank of first appearance in this lane
     if (!hash_only) {
         key_rank.reserve(256);
-        for (const auto& b : blocks) { const uint32_t k = io->write_key(b); key_rank.emplace(k, (uint32_t)key_rank.size()); }
+        for (const auto& b : blocks) { const uint32_t k = io->write_key(b); key_rank.emplace(k, (uint32_t)(key_rank.size() & 0xFFFFu)); }
     }
+    struct WriteSched {
+        std::mutex mu; std::condition_variable cv; bool closed = false;
+        std::vector<std::deque<IoTask>> fq; std::vector<uint8_t> busy, queued; std::deque<uint32_t> ready;
+        void init(size_t n) { fq.resize(n); busy.assign(n, 0); queued.assign(n, 0); }
+        void push(uint32_t r, const IoTask& t) {
+            { std::lock_guard<std::mutex> lk(mu); fq[r].push_back(t); if (!busy[r] && !queued[r]) { ready.push_back(r); queued[r] = 1; } }
+            cv.notify_one();
+        }
+        bool pop(uint32_t* r, IoTask* t) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return closed || !ready.empty(); });
+            if (ready.empty()) return false;
+            *r = ready.front(); ready.pop_front(); queued[*r] = 0; busy[*r] = 1;
+            *t = fq[*r].front(); fq[*r].pop_front();
+            return true;
+        }
+        void done(uint32_t r) {
+            bool more = false;
+            { std::lock_guard<std::mutex> lk(mu); busy[r] = 0; if (!fq[r].empty() && !queued[r]) { ready.push_back(r); queued[r] = 1; more = true; } }
+            if (more) cv.notify_one();
+        }
+        void close() { { std::lock_guard<std::mutex> lk(mu); closed = true; } cv.notify_all(); }
+    } wsched;
+    wsched.init(std::min<size_t>(std::max<size_t>(key_rank.size(), 1), 0x10000));
     BQ<Batch*> submit_q, hashwait_q, d2hwait_q;
     std::mutex done_mu; std::condition_variable done_cv; size_t batches_done = 0;
     std::mutex stat_mu;
@@ -768,19 +790,19 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
             }
             if (tasks.empty()) { finish_batch(b); continue; }
             b->writes_left.store((int)tasks.size());
-            for (auto& t : tasks) write_qs[key_rank[io->write_key(blocks[t.i0])] % n_writers]->push(t);
+            for (auto& t : tasks) wsched.push(key_rank[io->write_key(blocks[t.i0])], t);
         }
     });
 
     // ---- stage 6: writers
     std::vector<std::thread> writers;
     for (uint32_t t = 0; t < n_writers; t++)
-        writers.emplace_back([&, t] {
+        writers.emplace_back([&] {
             if (bind_io && bind_wr == 1) bind_thread(pipe->dev);
             else if (bind_io && bind_wr == 2) bind_thread_complement(pipe->dev);
             if (dev_dst) cudaSetDevice(pipe->dev.dev);
-            IoTask k;
-            while (write_qs[t]->pop(&k)) {
+            IoTask k; uint32_t krank = 0;
+            while (wsched.pop(&krank, &k)) {
                 Slot& sl = pipe->slots[k.batch->slot];
                 uint64_t wrote = 0;
                 const uint64_t w0 = now_ns();
@@ -791,6 +813,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
                     if (rc) { set_err(rc); break; }
                 }
                 wr_busy += now_ns() - w0;
+                wsched.done(krank);
                 { std::lock_guard<std::mutex> lk(stat_mu); stats->bytes_written += wrote; }
                 if (k.batch->writes_left.fetch_sub(1) == 1) finish_batch(k.batch);
             }
@@ -801,7 +824,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
         done_cv.wait(lk, [&] { return batches_done == n_batches; });
     }
     read_q.close(); submit_q.close(); hashwait_q.close(); d2hwait_q.close(); free_slots.close();
-    for (auto& q : write_qs) q->close();
+    wsched.close();
     dispatcher.join();
     for (auto& t : readers) t.join();
     submitter.join(); hashwaiter.join(); d2hwaiter.join();
