@@ -481,16 +481,19 @@ def main() -> None:
         clocks = ClockSampler(gpu)
 
         # ---------------- build the workload and the step
-        need_gib = {"1": 4, "2A": 32 * (world if world > 1 else 1) + (22 * world if world > 1 and not args.no_sharded else 0), "2B": 32,
+        need_gib = {"1": 4, "2A": 32 * (world if world > 1 else max(1, args.gpus)) + (22 * world if world > 1 and not args.no_sharded else 0), "2B": 32,
                     "3": 204, "4": 104, "5": 21 * args.callers + 4}[cfg]
         if rank == 0:
             require_memory(need_gib * GiB, f"config {cfg}")
         if cfg in ("2A", "2B"):
             if active:
                 src = base / "src"
-                nbytes = datagen("files", src, plan["seed"], 10, GiB) if cfg == "2A" else datagen("layer", src, 2, 10 * GiB, 40960)
-                mask = 1 << gpu if cfg == "2A" else 1
-                n_gpu_used = 1
+                # `--gpus N` WITHOUT torchrun: one process drives N GPUs, so the weak-scaled workload (N x 10 GiB) is ONE
+                # call sharded across them in-process; under torchrun every rank has its own 10 GiB tree and GPU
+                inproc_n = args.gpus if (world == 1 and cfg == "2A" and args.gpus > 1) else 1
+                nbytes = datagen("files", src, plan["seed"], 10 * inproc_n, GiB) if cfg == "2A" else datagen("layer", src, 2, 10 * GiB, 40960)
+                mask = (all_mask if inproc_n > 1 else 1 << gpu) if cfg == "2A" else 1
+                n_gpu_used = inproc_n
 
                 def step(i):
                     dst = fresh_dir(base / "dst")
@@ -672,12 +675,13 @@ def main() -> None:
             value = total_bytes / wall / GiB
             roof = hbm_resident_roofline(vm, 0, args.steps)
             link = vm.link_probe(0, 4 * GiB)
-            n_gpu_line = world if not solo else n_gpu_used
+            n_gpu_line = (world if world > 1 else n_gpu_used) if not solo else n_gpu_used
             roof["link"] = link_roofline(link, total_bytes, d2h_bytes * n_trees, wall, n_gpu_line, roof["peak"])
             roof["in_pipeline"] = {"launches_per_step": int(stats["kernel_launches"]), "mean_launch_ms": round(stats["ms_kernel"] / max(1, stats["kernel_launches"]), 3)
                                    if "ms_kernel" in stats else None,
                                    "note": "the e2e path hashes one staging slot per launch; launches of all slots overlap on side streams"}
-            par = (f"{world} independent trees, one per GPU/rank, no collective" if not solo else
+            par = (f"one process, ONE call over {n_gpu_used} GPUs, block list sharded in-process (whole files per lane)" if (not solo and world == 1 and n_gpu_used > 1) else
+                   f"{world} independent trees, one per GPU/rank, no collective" if not solo else
                    f"one process, {n_gpu_used} GPU(s)" + (f", {args.callers} caller threads" if cfg == "5" else ", block list sharded in-process"))
             line = {
                 "metric": METRIC, "value": round(value, 3), "unit": "GiB/s", "n_gpus": world if world > 1 else args.gpus,
