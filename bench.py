@@ -696,7 +696,7 @@ def main() -> None:
                         "d2h_bytes_per_step": int(d2h_bytes * n_trees), "ms_per_step": round(1e3 * wall, 1),
                         "api": "vmig_migrate_tree (utils.CopyDir drop-in) through the C ABI, tmpfs -> tmpfs, host files in and out",
                         "phases_ms": {k[3:]: round(stats[k] / 1e6, 1) for k in ("ns_walk", "ns_plan", "ns_data", "ns_meta", "ns_table")}},
-                "gpu_launches": int(launches), "parity_gate": gate,
+                "gpu_launches": int(launches * n_trees), "parity_gate": gate,
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
             }
             if sharded:
