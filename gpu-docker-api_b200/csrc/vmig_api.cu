@@ -330,7 +330,8 @@ int run_blocks(const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior,
     {
         std::unordered_map<uint32_t, int> seen;                  // blocks are interleaved across <= 64 files
         for (size_t i = 0; i < blocks.size() && i < 256; i++) seen[io->write_key(blocks[i])] = 1;
-        io_threads_default(&readers, &writers, o.io_threads, lanes, std::min(n_gpus, lanes), seen.size() >= 32, has_prior, hash_only);
+        // "many files" is a property of what ONE lane sees: 100 x 1 GiB over 8 lanes is 12 large files per lane
+        io_threads_default(&readers, &writers, o.io_threads, lanes, std::min(n_gpus, lanes), seen.size() / lanes >= 32, has_prior, hash_only);
     }
     std::atomic<int> err{0}; std::string err_msg; std::mutex err_mu;
     std::vector<LaneStats> ls(lanes);
