@@ -5,6 +5,7 @@
 #include "vmig_engine.h"
 #include "vmig_kernels.cuh"
 #include "vmig_cufile.h"
+#include "vmig_sched.h"
 
 #include <sched.h>
 #include <unistd.h>
@@ -545,29 +546,7 @@ int run_lane(Pipe* pipe, const std::vector<BlockRef>& blocks, BlockIO* io, bool 
         key_rank.reserve(256);
         for (const auto& b : blocks) { const uint32_t k = io->write_key(b); key_rank.emplace(k, (uint32_t)(key_rank.size() & 0xFFFFu)); }
     }
-    struct WriteSched {
-        std::mutex mu; std::condition_variable cv; bool closed = false;
-        std::vector<std::deque<IoTask>> fq; std::vector<uint8_t> busy, queued; std::deque<uint32_t> ready;
-        void init(size_t n) { fq.resize(n); busy.assign(n, 0); queued.assign(n, 0); }
-        void push(uint32_t r, const IoTask& t) {
-            { std::lock_guard<std::mutex> lk(mu); fq[r].push_back(t); if (!busy[r] && !queued[r]) { ready.push_back(r); queued[r] = 1; } }
-            cv.notify_one();
-        }
-        bool pop(uint32_t* r, IoTask* t) {
-            std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return closed || !ready.empty(); });
-            if (ready.empty()) return false;
-            *r = ready.front(); ready.pop_front(); queued[*r] = 0; busy[*r] = 1;
-            *t = fq[*r].front(); fq[*r].pop_front();
-            return true;
-        }
-        void done(uint32_t r) {
-            bool more = false;
-            { std::lock_guard<std::mutex> lk(mu); busy[r] = 0; if (!fq[r].empty() && !queued[r]) { ready.push_back(r); queued[r] = 1; more = true; } }
-            if (more) cv.notify_one();
-        }
-        void close() { { std::lock_guard<std::mutex> lk(mu); closed = true; } cv.notify_all(); }
-    } wsched;
+    KeyedQueue<IoTask> wsched;      // vmig_sched.h
     wsched.init(std::min<size_t>(std::max<size_t>(key_rank.size(), 1), 0x10000));
     BQ<Batch*> submit_q, hashwait_q, d2hwait_q;
     std::mutex done_mu; std::condition_variable done_cv; size_t batches_done = 0;

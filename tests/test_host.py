@@ -89,6 +89,17 @@ def test_source_side_path_safety_unit(shm_tmp):
     assert r.returncode == 0 and "tree unit ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_writer_queue_invariants(tmp_path):
+    """csrc/vmig_sched.h alone (no GPU): one worker per key at a time, per-key FIFO, every task exactly once."""
+    import subprocess
+    exe = tmp_path / "sched_unit"
+    csrc = ROOT / "gpu-docker-api_b200" / "csrc"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-pthread", "-I", str(csrc), str(ROOT / "tests" / "sched_unit.cpp"),
+                    "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "sched unit ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_struct_layouts_match_header(vm):
     assert ctypes.sizeof(vm.Opts) == 32
     assert ctypes.sizeof(vm.Stats) == 18 * 8 + 8 + 8 + 24
