@@ -44,7 +44,7 @@ EXPORTS = [
     "vmig_host_free", "vmig_hash_blocks", "vmig_resident_open", "vmig_resident_close", "vmig_resident_fill",
     "vmig_resident_set_len", "vmig_resident_upload", "vmig_resident_download", "vmig_resident_flip",
     "vmig_resident_set_prior", "vmig_resident_pass", "vmig_resident_results", "vmig_table_info_read",
-    "vmig_table_hashes", "vmig_dir_size", "vmig_to_bytes", "vmig_datagen_files", "vmig_manifest", "vmig_link_probe",
+    "vmig_table_hashes", "vmig_dir_size", "vmig_to_bytes", "vmig_datagen_files", "vmig_manifest", "vmig_link_probe", "vmig_thread_plan",
 ]
 
 
@@ -107,6 +107,7 @@ _sig = {
     "vmig_datagen_files": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32]),
     "vmig_manifest": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(Stats)]),
     "vmig_link_probe": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_double)]),
+    "vmig_thread_plan": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
 }
 for _n, (_r, _a) in _sig.items():
     _f = getattr(_lib, _n)
@@ -340,6 +341,13 @@ def link_probe(gpu: int = 0, nbytes: int = 4 << 30) -> dict:
     g = (C.c_double * 4)()
     _check(_lib.vmig_link_probe(gpu, nbytes, g), "vmig_link_probe")
     return {"h2d_GBps": g[0], "d2h_GBps": g[1], "duplex_h2d_GBps": g[2], "duplex_d2h_GBps": g[3]}
+
+
+def thread_plan(lanes: int = 1, n_gpus: int = 1, *, flags: int = 0, has_prior: bool = False):
+    """(readers, writers) per lane the engine would use on this box for such a call (no GPU needed)."""
+    r, w = C.c_uint32(0), C.c_uint32(0)
+    _check(_lib.vmig_thread_plan(lanes, n_gpus, flags, int(has_prior), C.byref(r), C.byref(w)), "vmig_thread_plan")
+    return r.value, w.value
 
 
 def manifest(src, out_table=None, *, flags: int = 0, block_bytes: int = 0) -> dict:

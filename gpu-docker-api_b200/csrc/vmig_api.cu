@@ -607,6 +607,12 @@ int vmig_move_dir(const char* src_dir, const char* dst_dir)
     return migrate_tree_impl(src_dir, dst_dir, nullptr, nullptr, &o, nullptr);
 }
 
+int vmig_thread_plan(uint32_t lanes, uint32_t n_gpus, uint32_t flags, int has_prior, uint32_t* readers, uint32_t* writers)
+{
+    if (!readers || !writers || !lanes || !n_gpus) return fail(VMIG_EINVAL, "bad thread-plan arguments");
+    return io_threads_default(readers, writers, 0, lanes, std::min<size_t>(n_gpus, lanes), false, has_prior != 0, (flags & VMIG_F_HASH_ONLY) != 0);
+}
+
 int vmig_host_alloc(void** p, uint64_t nbytes)
 {
     if (!p) return fail(VMIG_EINVAL, "null out pointer");

@@ -414,6 +414,7 @@ int io_threads_default(uint32_t* readers, uint32_t* writers, uint32_t requested,
     if (r <= 0 || w <= 0) {
         cpu_set_t cur; CPU_ZERO(&cur);
         long ncpu = sched_getaffinity(0, sizeof cur, &cur) == 0 ? CPU_COUNT(&cur) : sysconf(_SC_NPROCESSORS_ONLN);
+        ncpu = env_long("VMIG_PLAN_CPUS", ncpu);                  // test hook: plan as if the box had this many CPUs
         // The host's page-cache copy capacity is a property of the BOX, not of a lane: measured on the 2-socket bench box,
         // ONE GPU is served best by ~20 copy threads in total however many lanes share it (8 readers + 12 writers; 40
         // threads: 12.4 GiB/s instead of 19.3, 96 threads: 8.8 -- profiles/r02_sweep_lanes_1gpu.txt), and eight GPUs by

@@ -210,6 +210,12 @@ int  vmig_resident_results(vmig_resident* r, uint64_t* hashes /*n_blocks, nullab
  * GB/s = 1e9 bytes per second. */
 int vmig_link_probe(int gpu, uint64_t bytes, double gbs[4]);
 
+/* What the engine would use on THIS box right now: host reader / writer threads PER LANE for a call of `lanes` lanes on
+ * `n_gpus` GPUs (plain copy; has_prior = 1: diff path; flags & VMIG_F_HASH_ONLY: hash-only), given the per-box budget
+ * (20 copy threads for one GPU, 13 per GPU beyond, capped by the CPUs), the lanes other calls of this process have in
+ * flight, and VMIG_READERS / VMIG_WRITERS / VMIG_IO_SHARE.  No GPU needed; for operators and tests. */
+int vmig_thread_plan(uint32_t lanes, uint32_t n_gpus, uint32_t flags, int has_prior, uint32_t* readers, uint32_t* writers);
+
 /* ---- block table + host-side helpers (no GPU needed) ---------------------------------------- */
 /* Block-table file, little-endian:
  *   char[8] "VMIGBT02"; u32 block_bytes; u32 algo (1 = XXH64 seed 0); u64 n_files; u64 n_blocks;

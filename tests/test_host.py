@@ -91,6 +91,27 @@ def test_source_side_path_safety_unit(shm_tmp):
     assert r.returncode == 0 and "tree unit ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_copy_thread_budget_is_per_box_and_divided_among_lanes(vm, monkeypatch):
+    """The host's page-cache copy capacity belongs to the box: 20 copy threads for one GPU however many lanes share it,
+    13 per GPU beyond (profiles/r02_sweep_lanes_1gpu.txt, r01_e2e_rank_scaling.txt)."""
+    for k in ("VMIG_READERS", "VMIG_WRITERS", "VMIG_IO_SHARE"):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv("VMIG_PLAN_CPUS", "128")
+    assert vm.thread_plan(1, 1) == (8, 12)                       # one lane, one GPU
+    assert vm.thread_plan(2, 1) == (4, 6) and vm.thread_plan(4, 1) == (2, 3)      # lanes share the GPU's 20
+    assert vm.thread_plan(8, 8) == (5, 8)                        # 104 for eight GPUs, 13 per lane
+    assert vm.thread_plan(1, 1, flags=vm.F_HASH_ONLY) == (16, 1)
+    assert vm.thread_plan(1, 1, has_prior=True) == (12, 12)
+    monkeypatch.setenv("VMIG_IO_SHARE", "8")                     # one process per GPU (bench.py under torchrun)
+    assert vm.thread_plan(1, 1) == (5, 8)
+    monkeypatch.delenv("VMIG_IO_SHARE")
+    monkeypatch.setenv("VMIG_PLAN_CPUS", "8")                    # a small host caps the budget at 7/8 of its CPUs
+    r, w = vm.thread_plan(1, 1)
+    assert r + w <= 7 and r >= 2 and w >= 2
+    monkeypatch.setenv("VMIG_READERS", "3"), monkeypatch.setenv("VMIG_WRITERS", "9")
+    assert vm.thread_plan(4, 2) == (3, 9)                        # explicit per-lane counts win
+
+
 def test_writer_queue_invariants(tmp_path):
     """csrc/vmig_sched.h alone (no GPU): one worker per key at a time, per-key FIFO, every task exactly once."""
     import subprocess
