@@ -97,6 +97,11 @@ class ClockSampler:
 
 
 _CPU_WAIT = [lambda: None]       # set by dist_setup: a barrier that parks ranks on the CPU (gloo), not inside an NCCL kernel
+_BCAST = [lambda v: v]           # set by dist_setup: rank 0's value for everybody (gloo)
+
+
+def bcast_from_rank0(v):
+    return _BCAST[0](v)
 
 
 def cpu_barrier() -> None:
@@ -121,6 +126,12 @@ def dist_setup():
     import datetime
     cpu_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(minutes=30))
     _CPU_WAIT[0] = lambda: dist.barrier(group=cpu_group)
+
+    def bcast(v):
+        box = [v]
+        dist.broadcast_object_list(box, src=0, group=cpu_group)
+        return box[0]
+    _BCAST[0] = bcast
 
     def barrier():
         dist.barrier()
@@ -458,6 +469,12 @@ def main() -> None:
         # one process per GPU: tell each rank's engine how many migrations share the host's copy threads
         os.environ.setdefault("VMIG_IO_SHARE", str(world))
     active = plan["active"]
+    if world > 1 and cfg == "2A" and not args.no_sharded:
+        # rank 0's extra leg (one call over an N x 10 GiB tree) needs 22 GiB per GPU on top of the per-rank trees: drop it,
+        # on every rank alike, where the container's memory does not allow it rather than fail the whole run
+        fits = (32 + 22) * world * GiB <= 0.85 * mem_budget_bytes() if rank == 0 else None
+        if not bcast_from_rank0(fits):
+            args.no_sharded = True
     line = None
     base = fresh_dir(shm_base() / plan["tree"])
     mnt = None

@@ -32,6 +32,7 @@ def test_two_rank_barrier_and_max(tmp_path):
     # single-call configs (sharded call, caller threads): rank 0 drives every GPU of the box from ONE process
     assert all(outs[0]["active_solo"].values()) and not any(outs[1]["active_solo"].values())
     assert outs[0]["all_mask"] == 0b11
+    assert [o["agreed"] for o in outs] == ["decided-by-rank-0"] * 2      # every rank follows rank 0's decision
 
 
 def test_reference_arm_skips_on_nonzero_rank():
