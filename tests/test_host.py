@@ -2,6 +2,7 @@
 helpers agree with the oracle / the reference's Go helpers, and the data path FAILS LOUDLY
 without a GPU (no CPU fallback).  No compute is done here."""
 import ctypes
+import json
 import os
 import re
 import struct
@@ -207,6 +208,20 @@ def test_block_table_reader_accepts_good_and_rejects_bad(vm, orc, shm_tmp):
     _write_table(shm_tmp / "gap", [(b"a", 1, 0), (b"b", 1, 2)], [1, 2, 3])
     with pytest.raises(vm.VmigError):
         vm.table_info(shm_tmp / "gap")
+
+
+def test_block_table_golden_fixture(vm, orc):
+    """tests/golden/table_v2.vmig (committed bytes, written by make_table_golden.py): libvmig's reader and the oracle's parser
+    both return what the fixture's JSON says -- the on-disk format VMIGBT02 is pinned."""
+    g = ROOT / "tests" / "golden"
+    want = json.loads((g / "table_v2.json").read_text())
+    info = vm.table_info(g / "table_v2.vmig")
+    assert info == {k: want[k] for k in ("block_bytes", "algo", "n_files", "n_blocks", "bytes_total")}
+    assert [f"{int(h):016x}" for h in vm.table_hashes(g / "table_v2.vmig")] == want["hashes"]
+    t = orc.read_table(g / "table_v2.vmig")
+    assert [[rel.decode("utf-8"), size] for rel, size, _ in t["entries"]] == want["entries"]
+    assert [list(i) for i in t["identity"]] == want["identity"]
+    assert [f"{int(h):016x}" for h in t["hashes"]] == want["hashes"]
 
 
 def test_block_table_reader_survives_corruption(vm, shm_tmp):
