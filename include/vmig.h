@@ -96,11 +96,14 @@ const char* vmig_version(void);
                                            the page cache (two CPU copies per byte) is bypassed.  Falls back to
                                            buffered I/O per file where the filesystem refuses O_DIRECT.  Env
                                            VMIG_DIRECT_IO=1 sets it for every call.                              */
-#define VMIG_F_CUFILE            0x100u /* GPUDirect Storage ingest: source blocks are read with cuFileRead straight
-                                           into the HBM slot (no IN ring, no H2D copy); libcufile is dlopen()ed, the
-                                           call fails with VMIG_ENOTSUP-like VMIG_EINVAL if it is absent.  Without the
-                                           nvidia-fs kernel module libcufile runs in compatibility mode (POSIX read +
-                                           bounce buffer), which is functionally identical.  Env VMIG_CUFILE=1.     */
+#define VMIG_F_CUFILE            0x100u /* GPUDirect Storage: source blocks are read with cuFileRead straight into the
+                                           HBM slot (no IN ring, no H2D copy) and surviving blocks written with
+                                           cuFileWrite straight out of it (no D2H copy, no OUT ring).  libcufile is
+                                           dlopen()ed: VMIG_EINVAL if it cannot be loaded or its driver cannot be
+                                           opened, VMIG_EIO with libcufile's own reason if it refuses a descriptor
+                                           (inside containers it needs a udev-visible block device: DESIGN.md §10).
+                                           Without the nvidia-fs kernel module libcufile runs in its compatibility
+                                           mode (POSIX I/O + bounce buffers).  Env VMIG_CUFILE=1.                 */
 
 typedef struct vmig_opts {
     uint32_t gpu_mask;         /* 0 = every initialised GPU; blocks are sharded across the set   */
