@@ -84,6 +84,16 @@ int main(int argc, char** argv) {
         CHECK(access((outside + "/f").c_str(), F_OK) == 0 && access((outside + "/secret").c_str(), F_OK) == 0);   // the symlinks were unlinked, not followed
         CHECK(access((pdst + "/keep/sub/g").c_str(), F_OK) == 0 && access((pdst + "/top").c_str(), F_OK) == 0 && lstat((pdst + "/ln").c_str(), &lst) == 0);
         CHECK(prune_extras(pdst, pm, true, &n) == VMIG_OK && n == 0);
+        // an entry that changed TYPE since the destination was written is in the way and goes too: a file where the source
+        // now has a directory, a directory (with content) where the source now has a file, a directory where it has a symlink
+        CHECK(system(("mkdir -p " + psrc + "/flip_dir " + pdst + "/flip_file/inner " + pdst + "/ln2").c_str()) == 0);
+        put(psrc + "/flip_file", "now a file"); put(pdst + "/flip_dir", "was a file"); put(pdst + "/flip_file/inner/z", "z");
+        CHECK(symlink("top", (psrc + "/ln2").c_str()) == 0);
+        CHECK(walk_tree(psrc, 4096, false, &pm) == VMIG_OK);
+        CHECK(prune_extras(pdst, pm, false, &n) == VMIG_OK && n == 5);            // flip_dir (file), flip_file/{inner/z, inner}, flip_file, ln2 (dir)
+        struct stat fst;
+        CHECK(lstat((pdst + "/flip_dir").c_str(), &fst) != 0 && lstat((pdst + "/flip_file").c_str(), &fst) != 0 && lstat((pdst + "/ln2").c_str(), &fst) != 0);
+        CHECK(make_dirs(pdst, pm) == VMIG_OK && lstat((pdst + "/flip_dir").c_str(), &fst) == 0 && S_ISDIR(fst.st_mode));
     }
 
     // ---- the walk is the same whether the root's sub-directories are taken by one thread or by eight
