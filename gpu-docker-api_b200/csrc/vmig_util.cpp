@@ -6,6 +6,7 @@
 #include "vmig_table.h"
 #include "vmig_tree.h"
 
+#include <cctype>
 #include <dirent.h>
 #include <fcntl.h>
 #include <unistd.h>
@@ -114,6 +115,8 @@ int vmig_to_bytes(const char* s, int64_t* out)
     const size_t n = strlen(s);
     if (n < 3) return fail(VMIG_EINVAL, "cannot parse size '%s'", s);
     const std::string num(s, n - 2), unit(s + n - 2);
+    // strconv.ParseFloat takes no leading white space (strtod would skip it)
+    if (num.empty() || isspace((unsigned char)num[0])) return fail(VMIG_EINVAL, "cannot parse size '%s'", s);
     char* end = nullptr; errno = 0;
     const double v = strtod(num.c_str(), &end);
     if (end == num.c_str() || *end != 0 || errno == ERANGE) return fail(VMIG_EINVAL, "cannot parse size '%s'", s);

@@ -141,7 +141,7 @@ def test_to_bytes_matches_reference_rules(vm):
     assert vm.ToBytes("20GB") == 20 << 30
     assert vm.ToBytes("1.5MB") == int(1.5 * (1 << 20))
     assert vm.ToBytes("100KB") == 100 << 10 and vm.ToBytes("2TB") == 2 << 40
-    for bad in ["20gb", "GB", "12", "1PB", "x1GB"]:
+    for bad in ["20gb", "GB", "12", "1PB", "x1GB", " 1GB", "\t2MB", "1 GB", "1.5.5KB"]:
         with pytest.raises(vm.VmigError):
             vm.ToBytes(bad)
 
@@ -288,6 +288,81 @@ def test_manifest_pass_matches_oracle_walk(vm, orc, shm_tmp):
     assert all(not e[0].startswith(b".hidden_dir/") for e in orc.read_table(shm_tmp / "m2.vmig")["entries"])
     with pytest.raises(vm.VmigError):
         vm.manifest(shm_tmp / "nope")
+
+
+def test_manifest_matches_oracle_walk_on_random_trees(vm, orc, shm_tmp):
+    """Property test (hypothesis): for random directory trees -- awkward names, empty files and directories, sizes around the
+    block size (a tiny block size keeps the trees small), hard links across directories, symlinks -- the engine's manifest
+    (parallel walk) lists the same files, sizes and block layout as the oracle's independent walk, and DirSize / the used-bytes
+    figure agree with a plain os.walk."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    names = st.text(alphabet=st.sampled_from(list("abcXYZ019 ._-é#")), min_size=1, max_size=6).filter(lambda n: n not in (".", "..") and "/" not in n)
+    counter = [0]
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.lists(st.tuples(st.lists(names, min_size=0, max_size=3), names, st.integers(0, 3 * 4096 + 7), st.sampled_from(["file", "file", "file", "dir", "symlink", "hardlink"])),
+                    min_size=0, max_size=14))
+    def run(items):
+        counter[0] += 1
+        root = shm_tmp / f"t{counter[0]}"
+        root.mkdir()
+        made_files = []
+        for dirs, name, size, kind in items:
+            d = root.joinpath(*dirs) if dirs else root
+            try:
+                d.mkdir(parents=True, exist_ok=True)
+            except (FileExistsError, NotADirectoryError):
+                continue
+            p = d / name
+            if p.exists() or p.is_symlink():
+                continue
+            if kind == "file":
+                p.write_bytes(bytes(size)); made_files.append(p)
+            elif kind == "dir":
+                p.mkdir()
+            elif kind == "symlink":
+                os.symlink("some/where", p)
+            elif made_files:
+                os.link(made_files[0], p)
+        bb = 4096
+        stt = vm.manifest(root, shm_tmp / f"m{counter[0]}.vmig", block_bytes=bb)
+        entries, hashes = orc.block_table_of_tree(root, bb)
+        tab = orc.read_table(shm_tmp / f"m{counter[0]}.vmig")
+        assert tab["block_bytes"] == bb and tab["entries"] == entries and len(tab["hashes"]) == len(hashes)
+        want_bytes = sum(os.lstat(os.path.join(dp, f)).st_size for dp, _, fs in os.walk(root) for f in fs if not os.path.islink(os.path.join(dp, f)))
+        assert stt["bytes_total"] == want_bytes == sum(e[1] for e in entries)
+        assert stt["dirs"] == 1 + sum(len(ds) for _, ds, _ in os.walk(root))
+        assert vm.DirSize(str(root)) == sum(os.lstat(os.path.join(dp, f)).st_size for dp, _, fs in os.walk(root) for f in fs)
+    run()
+
+
+def test_to_bytes_property(vm):
+    """Property test: vmig_to_bytes == the reference's rule (utils/file.go:24-48: last two characters are the unit, the rest is
+    strconv.ParseFloat, 1024-based, truncated to int64) for random magnitudes and units; anything else is VMIG_EINVAL."""
+    from hypothesis import given, settings, strategies as st
+    mult = {"KB": 1 << 10, "MB": 1 << 20, "GB": 1 << 30, "TB": 1 << 40}
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.floats(min_value=0, max_value=4096, allow_nan=False, allow_infinity=False), st.sampled_from(sorted(mult)), st.integers(0, 3))
+    def ok(x, unit, digits):
+        text = f"{x:.{digits}f}{unit}"
+        assert vm.ToBytes(text) == int(float(f"{x:.{digits}f}") * mult[unit])
+    ok()
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.text(alphabet=st.sampled_from(list("0123456789.kKmMgGtTbBxX -")), min_size=0, max_size=8))
+    def bad(text):
+        good = len(text) >= 3 and text[-2:] in mult
+        try:
+            float(text[:-2]) if good else None
+            if good and (text[:-2].strip() != text[:-2] or text[:-2].lower() in ("inf", "nan") or "x" in text[:-2].lower()):
+                good = False
+        except ValueError:
+            good = False
+        if not good:
+            with pytest.raises(vm.VmigError):
+                vm.ToBytes(text)
+    bad()
 
 
 def test_reference_interface_resolvers(vm):
