@@ -274,7 +274,8 @@ bool is_pinned(const void* p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// run a block list over the selected GPUs (contiguous byte-balanced shares, one lane per GPU)
+// run a block list over the selected GPUs: n_gpus x lanes_per_gpu lanes, whole files per lane (LPT by bytes);
+// contiguous byte-balanced ranges only when there are fewer than two files per lane
 int run_blocks(const std::vector<BlockRef>& blocks, BlockIO* io, bool has_prior, bool hash_only, const vmig_opts& o,
                uint64_t* hashes, vmig_stats* st)
 {
