@@ -54,6 +54,25 @@ CONFIGS = {
 }
 
 
+_JSON_OUT = [None]
+
+
+def claim_stdout() -> None:
+    """The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner) and helpers write there
+    too, so the real stdout is kept aside for the result line and fd 1 is pointed at stderr for everything else."""
+    if _JSON_OUT[0] is None:
+        sys.stdout.flush()
+        _JSON_OUT[0] = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT[0] or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def shm_base() -> Path:
     return Path(os.environ.get("VMIG_BENCH_DIR", "/dev/shm"))
 
@@ -373,7 +392,7 @@ def run_reference(args) -> None:
                                  "sample": sample, "host_cpus": os.cpu_count()},
                 "e2e": {"value": round(v, 3), "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
     finally:
         if mnt:
             mnt.close()
@@ -454,6 +473,7 @@ def main() -> None:
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -722,7 +742,7 @@ def main() -> None:
                 line["per_call_GiBps"] = [round(10 * GiB / statistics.mean(t[args.warmup:]) / GiB, 2) for t in per_call]
             if mnt:
                 line["config"]["mounts"] = mnt.kind
-            print(json.dumps(line), flush=True)
+            emit(line)
     finally:
         if mnt:
             mnt.close()
